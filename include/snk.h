@@ -1,0 +1,190 @@
+/* snk.h -- C ABI of the B200-native batched multi-snake environment (libsnk.so).
+ *
+ * The reference (jdubkim/Self-play-on-Multi-Snakes-Environment) has no native boundary: its hot
+ * path is a per-instance Python `gym.Env` stepped by one OS process per env.  This header is the
+ * boundary a native replacement of that path exports; every entry point names the reference
+ * interface it replaces (paths relative to the reference's `src/`).  Plain pointers and sizes
+ * only -- no torch / Python types -- so it binds from ctypes, cffi, pybind11 or any FFI.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SNK_E* code; no exception crosses;
+ *     `snk_last_error()` gives the text of the calling thread's last failure.
+ *   - `d_` pointers are device memory of the handle's CUDA device, `h_` pointers are host memory.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  All device
+ *     work is stream-ordered on it; no entry point synchronises unless its comment says so.
+ *   - one handle per GPU (per shard of the global env range); a handle is not thread-safe.
+ *
+ * Geometry.  D = board edge, V = D + 2 (one-cell border).  A cell (x, y) -- x is the FIRST
+ * observation index, `ob[x+1][y+1]` in gym_snake/envs/snake_multiple_test.py:31 -- is stored as
+ * the padded id  pid = (x + 1) * V + (y + 1)  (uint16), which can also hold a head that is one
+ * step outside the board.
+ */
+#ifndef SNK_H_
+#define SNK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNK_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define SNK_OK 0
+#define SNK_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define SNK_ECUDA (-2)    /* CUDA runtime failure (text in snk_last_error) */
+#define SNK_ENOMEM (-3)
+#define SNK_ESTATE (-4)   /* device-side error flag raised (see SNK_DEVERR_*) */
+
+/* device error flags (sticky; read + cleared by snk_check_errors) */
+#define SNK_DEVERR_TAPE_UNDERRUN 1u   /* replay tape exhausted for some env */
+#define SNK_DEVERR_TAPE_BOUND 2u      /* replayed draw was recorded with another bound */
+#define SNK_DEVERR_FRUIT_OVERFLOW 4u  /* >255 fruits on one cell (adversarial / cut grid) */
+#define SNK_DEVERR_BODY_OVERFLOW 8u   /* ring capacity exceeded (cannot happen for cap = D*D+1) */
+
+/* rule-sets */
+#define SNK_RULES_CLASSIC 0      /* gym_snake/envs/snake_multiple_test.py  (SnakeEnv) */
+#define SNK_RULES_ADVERSARIAL 1  /* gym_snake/envs/snake_adversarial_env.py (dead body -> fruit, spare_fruits) */
+#define SNK_RULES_CUT 2          /* README.md:11 "body-cut"; no reference code -- spec in DESIGN.md, parity unpinned */
+
+/* observation modes */
+#define SNK_OBS_NATIVE 0   /* uint8 [N][V][V][3K], the reference's get_multi_snake_ob() stacked by np.stack */
+#define SNK_OBS_ATARI84 1  /* uint8 [N][84][84][3K]: utils.py:27-31 WarpFrame; exact when 84 % V == 0 */
+
+/* RNG modes */
+#define SNK_RNG_PHILOX 0   /* Philox4x32-10, key (seed, global env id), counter = per-env draw index */
+#define SNK_RNG_TAPE 1     /* replay recorded reference draws (snk_set_draw_tape) */
+
+/* Constructor arguments.  Replaces the env kwargs of
+ * gym_snake/envs/snake_multiple_env_new.py:10 (`size, n_snakes, n_fruits`), `Config.NUM_SNAKES`
+ * (config.py:16, read at snake_multiple_test.py:223), `env.seed(seed + rank)` (utils.py:39) and the
+ * `[make_env(i) for i in range(num_env)]` fan-out of utils.py:49. */
+typedef struct snk_config {
+  int32_t size;        /* D, 2..254 */
+  int32_t n_snakes;    /* S, 1..32 */
+  int32_t n_fruits;    /* F, 0..64; the reference uses F = S (snake_multiple_test.py:223-225) */
+  int32_t n_views;     /* K, 1..32; 0 = S.  SnakeEnv emits K = 3 (snake_multiple_test.py:93-95) */
+  int32_t rules;       /* SNK_RULES_* */
+  int32_t max_steps;   /* episode cap, reference 2000 (snake_multiple_test.py:195); 0 = 2000 */
+  int32_t auto_reset;  /* 1 = SubprocVecEnv worker contract (baselines/common/vec_env/subproc_vec_env.py:13-16) */
+  int32_t obs_mode;    /* SNK_OBS_* */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t rng_mode;    /* SNK_RNG_* */
+  int64_t num_envs;    /* N, envs held by THIS handle */
+  int64_t env_id_base; /* global id of this handle's env 0 (shard offset; keys the RNG) */
+  uint64_t seed;
+} snk_config;
+
+/* Device buffers owned by the handle (valid until snk_destroy).  Replaces the tuple returned by
+ * SubprocVecEnv.step_wait (subproc_vec_env.py:57-61) and Monitor's info['episode']
+ * (baselines/bench/monitor.py:62-76). */
+typedef struct snk_buffers {
+  uint8_t* d_obs;          /* [N][H][W][3K] uint8 (H = W = V native, 84 atari); may be redirected */
+  float* d_reward;         /* [N]    reward of snake 0 (the reference's scalar reward) */
+  float* d_reward_all;     /* [N][S] extension: per-snake reward */
+  uint8_t* d_done;         /* [N]    1 = episode ended this step (obs is then the reset obs if auto_reset) */
+  uint8_t* d_num_alive;    /* [N]    info['num_snakes'] */
+  float* d_episode_return; /* [N]    valid where d_done: Monitor 'r' */
+  int32_t* d_episode_len;  /* [N]    valid where d_done: Monitor 'l' */
+  double* d_stats;         /* [SNK_NSTATS] running sums since snk_reset_stats */
+  size_t obs_bytes;        /* N*H*W*3K */
+  int32_t obs_h, obs_w, obs_c;
+} snk_buffers;
+
+/* indices into d_stats / snk_get_stats */
+#define SNK_STAT_ENV_STEPS 0
+#define SNK_STAT_EPISODES 1
+#define SNK_STAT_RETURN_SUM 2
+#define SNK_STAT_LENGTH_SUM 3
+#define SNK_STAT_FRUITS 4     /* fruits eaten by any snake */
+#define SNK_STAT_DEATHS 5     /* snakes that died */
+#define SNK_STAT_BODY_CELLS 6 /* sum over env-steps of total live body length after the step (mean SigmaL = this / ENV_STEPS) */
+#define SNK_STAT_DRAWS 7      /* RNG draws consumed */
+#define SNK_NSTATS 8
+
+/* Offsets (bytes) of the canonical state arrays inside a snk_dump_state blob.  Bodies are stored
+ * head-first and zero-padded, so two blobs are byte-comparable. */
+typedef struct snk_state_layout {
+  size_t total_bytes;
+  size_t off_t;          /* int32  [N]       step counter t */
+  size_t off_spare;      /* uint32 [N]       adversarial spare_fruits (snake_adversarial_env.py:14) */
+  size_t off_draw_ctr;   /* uint32 [N]       draws consumed so far */
+  size_t off_ep_ret;     /* float  [N]       running episode return (Monitor) */
+  size_t off_ep_len;     /* int32  [N]       running episode length (Monitor) */
+  size_t off_len;        /* uint16 [N][S]    body length, 0 = dead */
+  size_t off_grow_to;    /* uint16 [N][S] */
+  size_t off_vel;        /* uint8  [N][S]    0 none, 1 +x, 2 +y, 3 -x, 4 -y */
+  size_t off_body;       /* uint16 [N][S][cap] padded ids, head first */
+  size_t off_fruit;      /* classic: uint16 [N][F] padded ids;  adversarial/cut: uint8 [N][V*V] counts */
+  int32_t cap;           /* D*D + 1 rounded up to a multiple of 8 */
+  int32_t fruit_is_grid; /* 0 list, 1 count grid */
+} snk_state_layout;
+
+typedef struct snk_handle snk_handle;
+
+int snk_version(void);
+const char* snk_last_error(void);
+
+/* gym.make(id) + env.__init__(**kwargs) + env.seed()  (utils.py:37-39), for N envs at once. */
+int snk_create(const snk_config* cfg, snk_handle** out);
+/* VecEnv.close()  (subproc_vec_env.py:73-83). */
+int snk_destroy(snk_handle* h);
+int snk_get_config(const snk_handle* h, snk_config* out);
+int snk_get_buffers(const snk_handle* h, snk_buffers* out);
+
+/* VecEnv.reset()  (subproc_vec_env.py:63-66 -> SnakeEnv.reset, snake_multiple_test.py:219-232).
+ * d_mask == NULL resets every env; otherwise only envs with d_mask[i] != 0 (their obs is rewritten,
+ * the others are left untouched). */
+int snk_reset(snk_handle* h, const uint8_t* d_mask, void* stream);
+
+/* VecEnv.step_async + step_wait  (subproc_vec_env.py:52-61 -> SnakeEnv.step,
+ * snake_multiple_test.py:166-197, get_multi_snake_ob :93-95, Monitor.step monitor.py:57-78).
+ * d_actions: int8 [N][S]; values outside the rule-set's action range are no-ops
+ * (snake_multiple_test.py:108-115).  One fused kernel launch. */
+int snk_step(snk_handle* h, const int8_t* d_actions, void* stream);
+
+/* Same step through HOST buffers, the shape in which SubprocVecEnv hands data to the learner
+ * (numpy arrays): copies actions H2D, steps, copies results D2H and synchronises `stream`.
+ * Any of the h_ output pointers may be NULL to skip that copy.  Host buffers should be pinned. */
+int snk_step_host(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, float* h_reward,
+                  uint8_t* h_done, uint8_t* h_num_alive, void* stream);
+
+/* Write observations straight into a caller-owned device buffer (e.g. slot t of the learner's
+ * rollout buffer, ppo_multi_agent_new.py:181) instead of the handle's own d_obs.
+ * NULL restores the internal buffer.  Must be 16-byte aligned. */
+int snk_set_obs_target(snk_handle* h, uint8_t* d_obs, size_t bytes);
+
+/* Replay mode: per-env tapes of the reference's np_random.randint draws
+ * (snake_multiple_test.py:200, :215).  CSR: env i owns vals/bounds[offsets[i] .. offsets[i+1]).
+ * Host arrays, copied to the device (synchronous).  Switches the handle to SNK_RNG_TAPE. */
+int snk_set_draw_tape(snk_handle* h, const uint32_t* h_vals, const uint32_t* h_bounds,
+                      const uint64_t* h_offsets);
+
+/* Canonical state (parity tests, checkpoint / resume).  Synchronous. */
+int snk_state_layout_of(const snk_config* cfg, snk_state_layout* out);
+int snk_dump_state(snk_handle* h, void* h_dst, size_t bytes);
+int snk_load_state(snk_handle* h, const void* h_src, size_t bytes);
+
+/* Episode statistics (Monitor's aggregate role).  snk_get_stats synchronises `stream`. */
+int snk_get_stats(snk_handle* h, double* h_stats /*[SNK_NSTATS]*/, void* stream);
+int snk_reset_stats(snk_handle* h, void* stream);
+/* Reads and clears the sticky device error flags (synchronises `stream`). */
+int snk_check_errors(snk_handle* h, uint32_t* flags, void* stream);
+
+/* Synthetic uniform action stream for benchmarks: Philox key (seed, global env id), stream 1,
+ * counter = step * S + snake, value in [0, n_actions).  d_actions: int8 [N][S]. */
+int snk_gen_actions(snk_handle* h, int8_t* d_actions, uint64_t step, uint64_t seed,
+                    int32_t n_actions, void* stream);
+
+/* Algorithmic bytes of one env-step: obs K*H*W*3 + state 19S + 2*SigmaL + 2F + 30. */
+int snk_algorithmic_bytes_per_step(const snk_config* cfg, double mean_sum_len, double* out);
+
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+int snk_launch_count(const snk_handle* h, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNK_H_ */
