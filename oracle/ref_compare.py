@@ -62,3 +62,27 @@ def lockstep(rules, S, D, steps, seed, action_seed, n_actions=5, load_state=None
             episodes += 1
             assert np.array_equal(ref.reset(), orc.reset()), ctx
     return steps, episodes
+
+
+def lockstep_scripted(rules, S, D, steps, seed):
+    """Like lockstep() but with the fruit-seeking script of make_golden.py; returns max body length seen."""
+    import ref_loader
+    from make_golden import scripted_action
+    ref = ref_loader.make_env(rules, S, D, np.random.RandomState(seed))
+    orc = SnakeOracle(D, S, S, 3, rules, draws=np.random.RandomState(seed))
+    cap = D * D + 1
+    assert np.array_equal(ref.reset(), orc.reset())
+    arng = np.random.RandomState(seed + 1)
+    max_len = 0
+    for i in range(steps):
+        a = np.array([scripted_action(ref, s, arng) for s in range(S)])
+        ob_r, r_r, d_r, info_r = ref.step(a)
+        ob_o, r_o, d_o, info_o = orc.step(a)
+        ctx = "%s S=%d D=%d step %d" % (rules, S, D, i)
+        assert np.array_equal(ob_r, ob_o), ctx
+        assert float(r_r) == float(r_o) and bool(d_r) == bool(d_o) and info_r["num_snakes"] == info_o["num_snakes"], ctx
+        assert_same_canonical(canonical_from_reference(ref, S, rules, cap), orc.canonical(cap), ctx)
+        max_len = max(max_len, max(len(b) for b in ref.state[0]))
+        if d_r:
+            assert np.array_equal(ref.reset(), orc.reset()), ctx
+    return max_len
