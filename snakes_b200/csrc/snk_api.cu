@@ -1,0 +1,386 @@
+// snk_api.cu -- the extern "C" boundary of libsnk.so (include/snk.h): handle lifetime, device
+// buffers, launch planning.  No torch, no Python: plain pointers and sizes.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "snk_device.cuh"
+#include "snk_launch.h"
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) return fail(SNK_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e));    \
+  } while (0)
+
+struct snk_handle {
+  snk_config cfg;
+  snk_state_layout lay;
+  Params p;
+  LaunchPlan plan;
+  int n_sm;
+  uint8_t* d_obs_own;
+  int8_t* d_actions_own;
+  uint8_t* d_blob;  // staging for dump / load
+  uint32_t* d_tape_vals;
+  uint32_t* d_tape_bounds;
+  uint64_t* d_tape_off;
+  std::vector<void*> allocs;
+  uint64_t launches;
+};
+
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+static int gcd(int a, int b) { return b ? gcd(b, a % b) : a; }
+
+static int cfg_check(const snk_config* c) {
+  if (!c) return fail(SNK_EINVAL, "config is NULL");
+  if (c->size < 2 || c->size > 254) return fail(SNK_EINVAL, "size must be 2..254, got %d", c->size);
+  if (c->n_snakes < 1 || c->n_snakes > 32) return fail(SNK_EINVAL, "n_snakes must be 1..32, got %d", c->n_snakes);
+  if (c->n_fruits < 0 || c->n_fruits > 32) return fail(SNK_EINVAL, "n_fruits must be 0..32, got %d", c->n_fruits);
+  if (c->n_views < 0 || c->n_views > 32) return fail(SNK_EINVAL, "n_views must be 0..32, got %d", c->n_views);
+  if (c->rules < 0 || c->rules > 2) return fail(SNK_EINVAL, "unknown rules %d", c->rules);
+  if (c->num_envs < 1) return fail(SNK_EINVAL, "num_envs must be >= 1");
+  if (c->max_steps < 0 || c->max_steps > 65535) return fail(SNK_EINVAL, "max_steps must be 0..65535");
+  if (c->obs_mode != SNK_OBS_NATIVE) return fail(SNK_EINVAL, "obs_mode %d not supported yet (native only)", c->obs_mode);
+  if (c->rng_mode != SNK_RNG_PHILOX && c->rng_mode != SNK_RNG_TAPE) return fail(SNK_EINVAL, "unknown rng_mode %d", c->rng_mode);
+  if ((uint64_t)(c->env_id_base + c->num_envs) > 0xffffffffull) return fail(SNK_EINVAL, "global env ids must fit 32 bits");
+  return SNK_OK;
+}
+
+extern "C" int snk_version(void) { return SNK_VERSION; }
+extern "C" const char* snk_last_error(void) { return g_err; }
+
+extern "C" int snk_state_layout_of(const snk_config* c, snk_state_layout* o) {
+  int rc = cfg_check(c);
+  if (rc) return rc;
+  if (!o) return fail(SNK_EINVAL, "layout is NULL");
+  const size_t N = (size_t)c->num_envs, S = (size_t)c->n_snakes, F = (size_t)c->n_fruits, D = (size_t)c->size, V = D + 2;
+  const int cap = (int)((D * D + 1 + 7) & ~(size_t)7);
+  size_t off = 0;
+  o->off_t = off;        off = align16(off + 4 * N);
+  o->off_spare = off;    off = align16(off + 4 * N);
+  o->off_draw_ctr = off; off = align16(off + 4 * N);
+  o->off_ep_ret = off;   off = align16(off + 4 * N);
+  o->off_ep_len = off;   off = align16(off + 4 * N);
+  o->off_len = off;      off = align16(off + 2 * N * S);
+  o->off_grow_to = off;  off = align16(off + 2 * N * S);
+  o->off_vel = off;      off = align16(off + N * S);
+  o->off_body = off;     off = align16(off + 2 * N * S * (size_t)cap);
+  o->off_fruit = off;
+  o->fruit_is_grid = c->rules != SNK_RULES_CLASSIC;
+  off = align16(off + (o->fruit_is_grid ? N * V * V : 2 * N * F));
+  o->total_bytes = off;
+  o->cap = cap;
+  return SNK_OK;
+}
+
+template <typename T>
+static int dev_alloc(snk_handle* h, T** out, size_t count, bool zero) {
+  void* ptr = nullptr;
+  const size_t bytes = align16(count * sizeof(T) + 16);
+  cudaError_t e = cudaMalloc(&ptr, bytes);
+  if (e != cudaSuccess) return fail(SNK_ENOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  h->allocs.push_back(ptr);
+  if (zero) CUDA_TRY(cudaMemset(ptr, 0, bytes));
+  *out = (T*)ptr;
+  return SNK_OK;
+}
+
+extern "C" int snk_destroy(snk_handle* h) {
+  if (!h) return SNK_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* q : h->allocs) cudaFree(q);
+  delete h;
+  return SNK_OK;
+}
+
+#define TRY(expr) do { int _rc = (expr); if (_rc) { snk_destroy(h); return _rc; } } while (0)
+#define CUDA_TRY_H(expr)                                                                        \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) { snk_destroy(h); return fail(SNK_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); } \
+  } while (0)
+
+extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
+  int rc = cfg_check(cfg);
+  if (rc) return rc;
+  if (!out) return fail(SNK_EINVAL, "out is NULL");
+  int n_dev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n_dev));
+  if (cfg->device < 0 || cfg->device >= n_dev) return fail(SNK_EINVAL, "device %d of %d", cfg->device, n_dev);
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  snk_handle* h = new snk_handle();
+  h->cfg = *cfg;
+  if (h->cfg.n_views == 0) h->cfg.n_views = cfg->n_snakes;
+  if (h->cfg.max_steps == 0) h->cfg.max_steps = 2000;
+  h->launches = 0;
+  h->d_obs_own = nullptr; h->d_actions_own = nullptr; h->d_blob = nullptr;
+  h->d_tape_vals = h->d_tape_bounds = nullptr; h->d_tape_off = nullptr;
+  snk_state_layout_of(&h->cfg, &h->lay);
+  cudaDeviceProp prop;
+  CUDA_TRY_H(cudaGetDeviceProperties(&prop, cfg->device));
+  h->n_sm = prop.multiProcessorCount;
+
+  Params& p = h->p;
+  memset(&p, 0, sizeof(p));
+  const int D = cfg->size, V = D + 2, S = cfg->n_snakes, F = cfg->n_fruits, K = h->cfg.n_views;
+  const long long N = cfg->num_envs;
+  p.D = D; p.V = V; p.VV = V * V; p.S = S; p.F = F; p.K = K; p.C = 3 * K;
+  p.cap = h->lay.cap;
+  p.RW = (REC_SNAKE0 + 2 * S + (F + 1) / 2 + 3) & ~3;
+  p.E = p.VV * p.C;
+  p.G = 16 / gcd(p.E, 16);
+  p.grid_stride = (int)align16((size_t)p.VV);
+  p.bm_words = (D * D + 31) / 32;
+  p.max_steps = h->cfg.max_steps; p.auto_reset = cfg->auto_reset != 0; p.rng_mode = cfg->rng_mode;
+  p.N = N; p.env_id_base = cfg->env_id_base; p.seed = cfg->seed;
+
+  // launch plan: tile kernel when W observations + template + scratch leave room for >= 2 CTAs per SM
+  LaunchPlan& plan = h->plan;
+  const int W = p.G > 8 ? p.G : 8;
+  const size_t smem_tile = (size_t)(W + p.G) * p.E + (size_t)W * (p.RW + p.bm_words) * 4;
+  const char* force = getenv("SNK_FORCE_KERNEL");  // "dense" or "tile": testing aid
+  plan.use_tile = smem_tile <= 110 * 1024;
+  if (force && !strcmp(force, "dense")) plan.use_tile = false;
+  if (plan.use_tile) {
+    p.W = W; plan.block = 32 * W; plan.smem = smem_tile;
+    p.n_groups = (N + W - 1) / W;
+  } else {
+    p.W = 1; plan.block = 256; plan.smem = align16((size_t)p.VV) + (size_t)(p.RW + p.bm_words) * 4;
+    p.n_groups = N;
+    if (plan.smem > 200 * 1024) { snk_destroy(h); return fail(SNK_EINVAL, "board too large for shared memory"); }
+  }
+  CUDA_TRY_H(snk_plan(cfg->rules, plan, h->n_sm));
+  plan.grid = (int)(p.n_groups < plan.max_grid ? p.n_groups : plan.max_grid);
+
+  // device buffers
+  TRY(dev_alloc(h, &p.rec, (size_t)N * p.RW, true));
+  TRY(dev_alloc(h, &p.body, (size_t)N * S * p.cap, true));
+  if (cfg->rules != SNK_RULES_CLASSIC) TRY(dev_alloc(h, &p.grid, (size_t)N * p.grid_stride, true));
+  TRY(dev_alloc(h, &h->d_obs_own, (size_t)N * p.E, true));
+  p.obs = h->d_obs_own;
+  TRY(dev_alloc(h, &p.reward, (size_t)N, true));
+  TRY(dev_alloc(h, &p.reward_all, (size_t)N * S, true));
+  TRY(dev_alloc(h, &p.done, (size_t)N, true));
+  TRY(dev_alloc(h, &p.num_alive, (size_t)N, true));
+  TRY(dev_alloc(h, &p.fin_ret, (size_t)N, true));
+  TRY(dev_alloc(h, &p.fin_len, (size_t)N, true));
+  TRY(dev_alloc(h, &p.stats, (size_t)SNK_NSTATS, true));
+  TRY(dev_alloc(h, &p.err, (size_t)1, true));
+  TRY(dev_alloc(h, &h->d_actions_own, (size_t)N * S, true));
+
+  // lookup tables: padded id -> (outside?, y-major board index incl. the reference's aliasing), and back
+  std::vector<uint32_t> cellinfo((size_t)p.VV);
+  std::vector<uint16_t> idx2pid((size_t)D * D);
+  for (int px = 0; px < V; ++px)
+    for (int py = 0; py < V; ++py) {
+      const int x = px - 1, y = py - 1;
+      const bool outside = x < 0 || x >= D || y < 0 || y >= D;
+      const long idx = (long)y * D + x;  // snake_multiple_test.py:209, not bounds-checked
+      uint32_t v = (idx >= 0 && idx < (long)D * D) ? (uint32_t)idx : 0x7fffffffu;
+      if (outside) v |= 0x80000000u;
+      cellinfo[(size_t)px * V + py] = v;
+      if (!outside) idx2pid[(size_t)idx] = (uint16_t)(px * V + py);
+    }
+  uint32_t* d_cellinfo; uint16_t* d_idx2pid; uint8_t* d_tmpl;
+  TRY(dev_alloc(h, &d_cellinfo, cellinfo.size(), false));
+  TRY(dev_alloc(h, &d_idx2pid, idx2pid.size(), false));
+  CUDA_TRY_H(cudaMemcpy(d_cellinfo, cellinfo.data(), cellinfo.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY_H(cudaMemcpy(d_idx2pid, idx2pid.data(), idx2pid.size() * 2, cudaMemcpyHostToDevice));
+  p.cellinfo = d_cellinfo; p.idx2pid = d_idx2pid;
+  // border-only observation of one 16-byte-aligned group of G envs (snake_multiple_test.py:52-56)
+  std::vector<uint8_t> tmpl((size_t)p.G * p.E, 0);
+  for (int g = 0; g < p.G; ++g)
+    for (int i = 0; i < V; ++i) {
+      const int ring_cells[4] = {i, (V - 1) * V + i, i * V, i * V + V - 1};
+      for (int q = 0; q < 4; ++q) memset(&tmpl[(size_t)g * p.E + (size_t)ring_cells[q] * p.C], 255, (size_t)p.C);
+    }
+  TRY(dev_alloc(h, &d_tmpl, tmpl.size(), false));
+  CUDA_TRY_H(cudaMemcpy(d_tmpl, tmpl.data(), tmpl.size(), cudaMemcpyHostToDevice));
+  p.tmpl = d_tmpl;
+  CUDA_TRY_H(cudaDeviceSynchronize());
+  *out = h;
+  return SNK_OK;
+}
+
+extern "C" int snk_get_config(const snk_handle* h, snk_config* out) {
+  if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
+  *out = h->cfg;
+  return SNK_OK;
+}
+
+extern "C" int snk_get_buffers(const snk_handle* h, snk_buffers* out) {
+  if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
+  const Params& p = h->p;
+  out->d_obs = p.obs; out->d_reward = p.reward; out->d_reward_all = p.reward_all; out->d_done = p.done;
+  out->d_num_alive = p.num_alive; out->d_episode_return = p.fin_ret; out->d_episode_len = p.fin_len;
+  out->d_stats = p.stats; out->obs_bytes = (size_t)p.N * p.E; out->obs_h = p.V; out->obs_w = p.V; out->obs_c = p.C;
+  return SNK_OK;
+}
+
+static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_t* d_mask, cudaStream_t stream) {
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  Params p = h->p;
+  p.mode = mode; p.actions = d_actions; p.mask = d_mask;
+  p.tape_vals = h->d_tape_vals; p.tape_bounds = h->d_tape_bounds; p.tape_off = h->d_tape_off;
+  if (p.rng_mode == SNK_RNG_TAPE && !p.tape_vals) return fail(SNK_EINVAL, "rng_mode is TAPE but no tape was set");
+  CUDA_TRY(snk_launch_step(p, h->cfg.rules, h->plan, stream));
+  h->launches++;
+  return SNK_OK;
+}
+
+extern "C" int snk_reset(snk_handle* h, const uint8_t* d_mask, void* stream) {
+  if (!h) return fail(SNK_EINVAL, "handle is NULL");
+  return launch(h, MODE_RESET, nullptr, d_mask, (cudaStream_t)stream);
+}
+
+extern "C" int snk_step(snk_handle* h, const int8_t* d_actions, void* stream) {
+  if (!h || !d_actions) return fail(SNK_EINVAL, "NULL argument");
+  return launch(h, MODE_STEP, d_actions, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int snk_step_host(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, float* h_reward, uint8_t* h_done,
+                             uint8_t* h_num_alive, void* stream) {
+  if (!h || !h_actions) return fail(SNK_EINVAL, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const Params& p = h->p;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpyAsync(h->d_actions_own, h_actions, (size_t)p.N * p.S, cudaMemcpyHostToDevice, s));
+  int rc = launch(h, MODE_STEP, h->d_actions_own, nullptr, s);
+  if (rc) return rc;
+  if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, p.reward, (size_t)p.N * 4, cudaMemcpyDeviceToHost, s));
+  if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, p.done, (size_t)p.N, cudaMemcpyDeviceToHost, s));
+  if (h_num_alive) CUDA_TRY(cudaMemcpyAsync(h_num_alive, p.num_alive, (size_t)p.N, cudaMemcpyDeviceToHost, s));
+  if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, p.obs, (size_t)p.N * p.E, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return SNK_OK;
+}
+
+extern "C" int snk_set_obs_target(snk_handle* h, uint8_t* d_obs, size_t bytes) {
+  if (!h) return fail(SNK_EINVAL, "handle is NULL");
+  if (!d_obs) { h->p.obs = h->d_obs_own; return SNK_OK; }
+  if (((uintptr_t)d_obs & 15) != 0) return fail(SNK_EINVAL, "obs target must be 16-byte aligned");
+  if (bytes < (size_t)h->p.N * h->p.E) return fail(SNK_EINVAL, "obs target too small: %zu < %zu", bytes, (size_t)h->p.N * h->p.E);
+  h->p.obs = d_obs;
+  return SNK_OK;
+}
+
+extern "C" int snk_set_draw_tape(snk_handle* h, const uint32_t* h_vals, const uint32_t* h_bounds, const uint64_t* h_offsets) {
+  if (!h || !h_vals || !h_offsets) return fail(SNK_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t N = (size_t)h->p.N, n = (size_t)h_offsets[N];
+  int rc;
+  if ((rc = dev_alloc(h, &h->d_tape_vals, n + 1, false))) return rc;
+  if ((rc = dev_alloc(h, &h->d_tape_off, N + 1, false))) return rc;
+  CUDA_TRY(cudaMemcpy(h->d_tape_vals, h_vals, n * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->d_tape_off, h_offsets, (N + 1) * 8, cudaMemcpyHostToDevice));
+  h->d_tape_bounds = nullptr;
+  if (h_bounds) {
+    if ((rc = dev_alloc(h, &h->d_tape_bounds, n + 1, false))) return rc;
+    CUDA_TRY(cudaMemcpy(h->d_tape_bounds, h_bounds, n * 4, cudaMemcpyHostToDevice));
+  }
+  h->p.rng_mode = SNK_RNG_TAPE;
+  return SNK_OK;
+}
+
+static int ensure_blob(snk_handle* h) {
+  if (h->d_blob) return SNK_OK;
+  return dev_alloc(h, &h->d_blob, h->lay.total_bytes, true);
+}
+
+extern "C" int snk_dump_state(snk_handle* h, void* h_dst, size_t bytes) {
+  if (!h || !h_dst) return fail(SNK_EINVAL, "NULL argument");
+  if (bytes < h->lay.total_bytes) return fail(SNK_EINVAL, "buffer too small: %zu < %zu", bytes, h->lay.total_bytes);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc = ensure_blob(h);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemset(h->d_blob, 0, h->lay.total_bytes));
+  CUDA_TRY(snk_launch_dump(h->p, h->d_blob, h->lay, 0));
+  h->launches++;
+  CUDA_TRY(cudaMemcpy(h_dst, h->d_blob, h->lay.total_bytes, cudaMemcpyDeviceToHost));
+  return SNK_OK;
+}
+
+extern "C" int snk_load_state(snk_handle* h, const void* h_src, size_t bytes) {
+  if (!h || !h_src) return fail(SNK_EINVAL, "NULL argument");
+  if (bytes < h->lay.total_bytes) return fail(SNK_EINVAL, "buffer too small: %zu < %zu", bytes, h->lay.total_bytes);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc = ensure_blob(h);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(h->d_blob, h_src, h->lay.total_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(snk_launch_load(h->p, h->d_blob, h->lay, 0));
+  h->launches++;
+  CUDA_TRY(cudaDeviceSynchronize());
+  return SNK_OK;
+}
+
+extern "C" int snk_get_stats(snk_handle* h, double* h_stats, void* stream) {
+  if (!h || !h_stats) return fail(SNK_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpyAsync(h_stats, h->p.stats, sizeof(double) * SNK_NSTATS, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return SNK_OK;
+}
+
+extern "C" int snk_reset_stats(snk_handle* h, void* stream) {
+  if (!h) return fail(SNK_EINVAL, "handle is NULL");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemsetAsync(h->p.stats, 0, sizeof(double) * SNK_NSTATS, (cudaStream_t)stream));
+  return SNK_OK;
+}
+
+extern "C" int snk_check_errors(snk_handle* h, uint32_t* flags, void* stream) {
+  if (!h || !flags) return fail(SNK_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpyAsync(flags, h->p.err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaMemsetAsync(h->p.err, 0, 4, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return SNK_OK;
+}
+
+extern "C" int snk_gen_actions(snk_handle* h, int8_t* d_actions, uint64_t step, uint64_t seed, int32_t n_actions, void* stream) {
+  if (!h || !d_actions || n_actions < 1) return fail(SNK_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(snk_launch_gen_actions(d_actions, h->p.N, h->p.S, h->p.env_id_base, step, seed, n_actions, (cudaStream_t)stream));
+  h->launches++;
+  return SNK_OK;
+}
+
+extern "C" int snk_algorithmic_bytes_per_step(const snk_config* c, double mean_sum_len, double* out) {
+  int rc = cfg_check(c);
+  if (rc) return rc;
+  if (!out) return fail(SNK_EINVAL, "out is NULL");
+  const double V = c->size + 2.0, S = c->n_snakes, F = c->n_fruits, K = c->n_views ? c->n_views : c->n_snakes;
+  *out = K * V * V * 3.0 + 19.0 * S + 2.0 * mean_sum_len + 2.0 * F + 30.0;
+  return SNK_OK;
+}
+
+extern "C" int snk_launch_count(const snk_handle* h, uint64_t* out) {
+  if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
+  *out = h->launches;
+  return SNK_OK;
+}
+
+extern "C" int snk_launch_info(const snk_handle* h, int32_t* out /*[6]: use_tile, grid, block, smem, occupancy, W*/) {
+  if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
+  out[0] = h->plan.use_tile; out[1] = h->plan.grid; out[2] = h->plan.block; out[3] = (int32_t)h->plan.smem;
+  out[4] = h->plan.occupancy; out[5] = h->p.W;
+  return SNK_OK;
+}

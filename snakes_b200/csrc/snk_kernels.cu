@@ -1,0 +1,343 @@
+// snk_kernels.cu -- the fused env-step kernels (sm_100a) and their launchers.
+//
+// k_step_tile  : one WARP per env, W consecutive envs per CTA, persistent grid.  The CTA keeps a
+//                shared-memory image of its W observations; each iteration restores it from a
+//                border-only template, the warps paint the few non-background cells of their env,
+//                and ONE thread hands the whole image to the TMA engine
+//                (cp.async.bulk.global.shared::cta) which streams it to HBM while the warps are
+//                already stepping the next group.  SM issue slots go to game logic, not to stores.
+// k_step_dense : one CTA per env for boards whose observation does not fit the tile scheme
+//                (e.g. 16 snakes on 64x64: 209 KB per env); same logic, cell-code grid in shared
+//                memory, dense colour mapping with coalesced stores.
+// Both fuse: action decode, head advance, eating + respawn, simultaneous collision test, body
+// clearing, reward / done, Monitor accounting, in-place auto-reset and the RGB encoding of
+// all K views (reference: gym_snake/envs/snake_multiple_test.py:166-197 + :35-58 + :93-95).
+#include "snk_device.cuh"
+#include "snk_launch.h"
+
+// ------------------------------------------------------------------ TMA bulk-copy wrappers
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, u32 bytes) {
+  const u32 s = (u32)__cvta_generic_to_shared(ssrc);
+  const u64 g = (u64)__cvta_generic_to_global(gdst);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void flush_stats(const Params& p, const WarpStats& st, u32 errs, double* s_stats, int lane) {
+  if (lane == 0) {
+    atomicAdd(&s_stats[SNK_STAT_ENV_STEPS], (double)st.steps);
+    atomicAdd(&s_stats[SNK_STAT_EPISODES], (double)st.episodes);
+    atomicAdd(&s_stats[SNK_STAT_RETURN_SUM], (double)st.ret_sum);
+    atomicAdd(&s_stats[SNK_STAT_LENGTH_SUM], (double)st.len_sum);
+    atomicAdd(&s_stats[SNK_STAT_FRUITS], (double)st.fruits);
+    atomicAdd(&s_stats[SNK_STAT_DEATHS], (double)st.deaths);
+    atomicAdd(&s_stats[SNK_STAT_BODY_CELLS], (double)st.cells);
+    atomicAdd(&s_stats[SNK_STAT_DRAWS], (double)st.draws);
+    if (errs) atomicOr(p.err, errs);
+  }
+}
+
+template <int RULES>
+__device__ __forceinline__ void advance_env(const Params& p, long long e, int lane, u32* sc, u32* bm, u32& errs, WarpStats& st) {
+  u16* rings = p.body + e * p.S * p.cap;
+  u8* grid = p.grid ? p.grid + e * p.grid_stride : nullptr;
+  load_rec(p, e, lane, sc);
+  if (p.mode == MODE_STEP) {
+    step_env_warp<RULES>(p, e, lane, sc, bm, rings, grid, errs, st);
+  } else if (p.mode == MODE_RESET) {
+    if (!p.mask || p.mask[e]) reset_env_warp<RULES>(p, e, lane, sc, rings, grid, errs, st);
+  }
+  __syncwarp();
+  if (p.mode != MODE_OBSERVE) store_rec(p, e, lane, sc);
+}
+
+// Paint the non-background cells of env e into its slot of the CTA's observation image
+// (get_ob_for_snake :35-58): fruits first, then snakes in index order (a later snake overwrites an
+// earlier one and any fruit), head over body.  The border is already in the image and is never
+// touched: cells outside the board are skipped, which equals the reference painting them and then
+// overwriting them with the wall (:52-56).  Interleaved layout: pixel pid, view k at pid*3K + 3k.
+template <int RULES>
+__device__ __forceinline__ void paint_env(const Params& p, long long e, int lane, const u32* sc, u8* img) {
+  const int S = p.S, F = p.F, K = p.K, C = p.C, cap = p.cap;
+  if (RULES == SNK_RULES_CLASSIC) {
+    const u16* fr = reinterpret_cast<const u16*>(sc + REC_SNAKE0 + 2 * S);
+    if (lane < F) {
+      u8* px = img + (int)fr[lane] * C;
+      for (int k = 0; k < K; ++k) px[3 * k] = 255;  // G and B of the restored image are 0
+    }
+  } else {
+    const u8* grid = p.grid + e * p.grid_stride;
+    for (int pid = lane; pid < p.VV; pid += 32) {
+      if (grid[pid] && !(__ldg(p.cellinfo + pid) >> 31)) {
+        u8* px = img + pid * C;
+        for (int k = 0; k < K; ++k) px[3 * k] = 255;
+      }
+    }
+  }
+  __syncwarp();
+  const u16* rings = p.body + e * S * cap;
+  for (int s = 0; s < S; ++s) {
+    const u32 a = sc[REC_SNAKE0 + 2 * s];
+    const int len = a >> 16, hs = a & 0xffff;
+    if (len == 0) continue;
+    for (int i = lane; i < len; i += 32) {
+      u8* px = img + ring_at(rings + s * cap, hs, i, cap) * C;
+      for (int k = 0; k < K; ++k) {
+        const u32 rgb = snake_rgb(s == k, i == 0);
+        px[3 * k] = (u8)rgb; px[3 * k + 1] = (u8)(rgb >> 8); px[3 * k + 2] = (u8)(rgb >> 16);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int RULES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_step_tile(const Params p) {
+  extern __shared__ __align__(128) u8 smem[];
+  __shared__ double s_stats[SNK_NSTATS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  const int W = p.W, E = p.E;
+  const int tile_bytes = W * E, tmpl_bytes = p.G * E;  // both multiples of 16
+  u8* tile = smem;
+  u8* tmpl = smem + tile_bytes;
+  u32* sc = reinterpret_cast<u32*>(tmpl + tmpl_bytes) + warp * (p.RW + p.bm_words);
+  u32* bm = sc + p.RW;
+  if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.tmpl);
+    uint4* dst = reinterpret_cast<uint4*>(tmpl);
+    for (int i = tid; i < tmpl_bytes / 16; i += nthr) dst[i] = src[i];
+  }
+  __syncthreads();
+  WarpStats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  u32 errs = 0;
+  for (long long grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+    const long long e = grp * W + warp;
+    const bool valid = e < p.N;
+    if (valid) advance_env<RULES>(p, e, lane, sc, bm, errs, st);
+    if (tid == 0) bulk_wait_read();  // the TMA engine has finished reading the previous image
+    __syncthreads();
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(tmpl);
+      const int n16 = tmpl_bytes / 16;
+      for (int c = 0; c < W / p.G; ++c) {
+        uint4* dst = reinterpret_cast<uint4*>(tile + c * tmpl_bytes);
+        for (int i = tid; i < n16; i += nthr) dst[i] = src[i];
+      }
+    }
+    __syncthreads();
+    if (valid) paint_env<RULES>(p, e, lane, sc, tile + warp * E);
+    fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
+    __syncthreads();
+    u8* gdst = p.obs + grp * (long long)tile_bytes;
+    if ((grp + 1) * W <= p.N) {
+      if (tid == 0) {
+        for (int off = 0; off < tile_bytes; off += 16384)
+          bulk_store_s2g(gdst + off, tile + off, (u32)min(16384, tile_bytes - off));
+        bulk_commit();
+      }
+    } else {  // last, partial group: plain stores for the valid envs only
+      const int bytes = (int)(p.N - grp * W) * E;
+      for (int b = tid; b < bytes; b += nthr) gdst[b] = tile[b];
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+  flush_stats(p, st, errs, s_stats, lane);
+  __syncthreads();
+  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+}
+
+template <int RULES>
+__global__ void __launch_bounds__(256) k_step_dense(const Params p) {
+  extern __shared__ __align__(128) u8 smem[];
+  __shared__ double s_stats[SNK_NSTATS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  const int S = p.S, F = p.F, K = p.K, VV = p.VV, V = p.V, cap = p.cap;
+  u8* code = smem;  // [VV] 0 empty, 1 fruit, 2 wall, 3+2s body of s, 4+2s head of s
+  u32* sc = reinterpret_cast<u32*>(smem + ((VV + 15) & ~15));
+  u32* bm = sc + p.RW;
+  if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  __syncthreads();
+  WarpStats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  u32 errs = 0;
+  for (long long e = blockIdx.x; e < p.N; e += gridDim.x) {
+    if (warp == 0) advance_env<RULES>(p, e, lane, sc, bm, errs, st);
+    for (int i = tid; i < VV; i += nthr) code[i] = 0;
+    __syncthreads();
+    if (RULES == SNK_RULES_CLASSIC) {
+      const u16* fr = reinterpret_cast<const u16*>(sc + REC_SNAKE0 + 2 * S);
+      if (tid < F) code[fr[tid]] = 1;
+    } else {
+      const u8* grid = p.grid + e * p.grid_stride;
+      for (int i = tid; i < VV; i += nthr) if (grid[i]) code[i] = 1;
+    }
+    __syncthreads();
+    const u16* rings = p.body + e * S * cap;
+    for (int s = 0; s < S; ++s) {
+      const u32 a = sc[REC_SNAKE0 + 2 * s];
+      const int len = a >> 16, hs = a & 0xffff;
+      if (len == 0) continue;  // block-uniform
+      for (int i = tid; i < len; i += nthr) code[ring_at(rings + s * cap, hs, i, cap)] = (u8)(3 + 2 * s + (i == 0));
+      __syncthreads();
+    }
+    for (int i = tid; i < V; i += nthr) {
+      code[i] = 2; code[(V - 1) * V + i] = 2; code[i * V] = 2; code[i * V + V - 1] = 2;
+    }
+    __syncthreads();
+    u8* out = p.obs + e * (long long)p.E;
+    for (int j = tid; j < VV * K; j += nthr) {  // j = pixel * K + view: 3 consecutive bytes
+      const int px = j / K, k = j - px * K;
+      const int c = code[px];
+      u32 rgb = 0;
+      if (c == 1) rgb = 255u;
+      else if (c == 2) rgb = 0xffffffu;
+      else if (c >= 3) rgb = snake_rgb(((c - 3) >> 1) == k, (c - 3) & 1);
+      out[3 * j] = (u8)rgb; out[3 * j + 1] = (u8)(rgb >> 8); out[3 * j + 2] = (u8)(rgb >> 16);
+    }
+    __syncthreads();
+  }
+  if (warp == 0) flush_stats(p, st, errs, s_stats, lane);
+  __syncthreads();
+  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+}
+
+// ------------------------------------------------------------------ state dump / load, action stream
+// canonical blob <-> private layout; one thread per (env, snake); not on the hot path
+__global__ void k_dump(const Params p, u8* blob, snk_state_layout lay) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int S = p.S, cap = p.cap;
+  if (i >= p.N * S) return;
+  const long long e = i / S;
+  const int s = (int)(i - e * S);
+  const u32* r = p.rec + e * p.RW;
+  const u32 a = r[REC_SNAKE0 + 2 * s], b = r[REC_SNAKE0 + 2 * s + 1];
+  const int len = a >> 16, hs = a & 0xffff;
+  reinterpret_cast<u16*>(blob + lay.off_len)[i] = (u16)len;
+  reinterpret_cast<u16*>(blob + lay.off_grow_to)[i] = (u16)(b & 0xffff);
+  (blob + lay.off_vel)[i] = (u8)(b >> 16);
+  u16* dst = reinterpret_cast<u16*>(blob + lay.off_body) + i * cap;
+  const u16* ring = p.body + i * cap;
+  for (int k = 0; k < cap; ++k) dst[k] = k < len ? (u16)ring_at(ring, hs, k, cap) : (u16)0;
+  if (s == 0) {
+    reinterpret_cast<int32_t*>(blob + lay.off_t)[e] = (int32_t)r[REC_T];
+    reinterpret_cast<u32*>(blob + lay.off_spare)[e] = r[REC_SPARE];
+    reinterpret_cast<u32*>(blob + lay.off_draw_ctr)[e] = r[REC_DRAW_CTR];
+    reinterpret_cast<u32*>(blob + lay.off_ep_ret)[e] = r[REC_EP_RET];
+    reinterpret_cast<int32_t*>(blob + lay.off_ep_len)[e] = (int32_t)r[REC_EP_LEN];
+    if (lay.fruit_is_grid) {
+      for (int k = 0; k < p.VV; ++k) (blob + lay.off_fruit)[e * p.VV + k] = p.grid[e * p.grid_stride + k];
+    } else {
+      const u16* fr = reinterpret_cast<const u16*>(r + REC_SNAKE0 + 2 * S);
+      for (int k = 0; k < p.F; ++k) reinterpret_cast<u16*>(blob + lay.off_fruit)[e * p.F + k] = fr[k];
+    }
+  }
+}
+
+__global__ void k_load(const Params p, const u8* blob, snk_state_layout lay) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int S = p.S, cap = p.cap;
+  if (i >= p.N * S) return;
+  const long long e = i / S;
+  const int s = (int)(i - e * S);
+  u32* r = p.rec + e * p.RW;
+  const u32 len = reinterpret_cast<const u16*>(blob + lay.off_len)[i];
+  const u32 grow = reinterpret_cast<const u16*>(blob + lay.off_grow_to)[i];
+  const u32 vel = (blob + lay.off_vel)[i];
+  r[REC_SNAKE0 + 2 * s] = 0u | (len << 16);
+  r[REC_SNAKE0 + 2 * s + 1] = grow | (vel << 16);
+  const u16* src = reinterpret_cast<const u16*>(blob + lay.off_body) + i * cap;
+  u16* ring = p.body + i * cap;
+  for (int k = 0; k < cap; ++k) ring[k] = src[k];
+  if (s == 0) {
+    r[REC_T] = (u32) reinterpret_cast<const int32_t*>(blob + lay.off_t)[e];
+    r[REC_SPARE] = reinterpret_cast<const u32*>(blob + lay.off_spare)[e];
+    r[REC_DRAW_CTR] = reinterpret_cast<const u32*>(blob + lay.off_draw_ctr)[e];
+    r[REC_EP_RET] = reinterpret_cast<const u32*>(blob + lay.off_ep_ret)[e];
+    r[REC_EP_LEN] = (u32) reinterpret_cast<const int32_t*>(blob + lay.off_ep_len)[e];
+    r[5] = r[6] = r[7] = 0;
+    if (lay.fruit_is_grid) {
+      for (int k = 0; k < p.VV; ++k) p.grid[e * p.grid_stride + k] = (blob + lay.off_fruit)[e * p.VV + k];
+    } else {
+      u16* fr = reinterpret_cast<u16*>(r + REC_SNAKE0 + 2 * S);
+      for (int k = 0; k < p.F; ++k) fr[k] = reinterpret_cast<const u16*>(blob + lay.off_fruit)[e * p.F + k];
+    }
+  }
+}
+
+__global__ void k_gen_actions(int8_t* actions, long long N, int S, long long env_id_base, u64 step, u64 seed, int n_actions) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N * S) return;
+  const long long e = i / S;
+  const int s = (int)(i - e * S);
+  actions[i] = (int8_t)philox_bounded(seed, (u64)(env_id_base + e), 1, step * (u64)S + (u64)s, (u32)n_actions);
+}
+
+// ------------------------------------------------------------------ launchers
+template <int RULES>
+static cudaError_t launch_rules(const Params& p, const LaunchPlan& plan, cudaStream_t stream) {
+  if (plan.use_tile) {
+    if (plan.block <= 256) k_step_tile<RULES, 256><<<plan.grid, plan.block, plan.smem, stream>>>(p);
+    else k_step_tile<RULES, 512><<<plan.grid, plan.block, plan.smem, stream>>>(p);
+  } else {
+    k_step_dense<RULES><<<plan.grid, plan.block, plan.smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, cudaStream_t stream) {
+  switch (rules) {
+    case SNK_RULES_CLASSIC: return launch_rules<SNK_RULES_CLASSIC>(p, plan, stream);
+    case SNK_RULES_ADVERSARIAL: return launch_rules<SNK_RULES_ADVERSARIAL>(p, plan, stream);
+    default: return launch_rules<SNK_RULES_CUT>(p, plan, stream);
+  }
+}
+
+template <int RULES>
+static cudaError_t plan_rules(LaunchPlan& plan, int n_sm) {
+  cudaError_t err;
+  int occ = 0;
+  if (plan.use_tile && plan.block <= 256) {
+    if ((err = cudaFuncSetAttribute(k_step_tile<RULES, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_tile<RULES, 256>, plan.block, plan.smem))) return err;
+  } else if (plan.use_tile) {
+    if ((err = cudaFuncSetAttribute(k_step_tile<RULES, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_tile<RULES, 512>, plan.block, plan.smem))) return err;
+  } else {
+    if ((err = cudaFuncSetAttribute(k_step_dense<RULES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_dense<RULES>, plan.block, plan.smem))) return err;
+  }
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  plan.occupancy = occ;
+  plan.max_grid = n_sm * occ;
+  return cudaSuccess;
+}
+
+cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm) {
+  switch (rules) {
+    case SNK_RULES_CLASSIC: return plan_rules<SNK_RULES_CLASSIC>(plan, n_sm);
+    case SNK_RULES_ADVERSARIAL: return plan_rules<SNK_RULES_ADVERSARIAL>(plan, n_sm);
+    default: return plan_rules<SNK_RULES_CUT>(plan, n_sm);
+  }
+}
+
+cudaError_t snk_launch_dump(const Params& p, u8* blob, const snk_state_layout& lay, cudaStream_t stream) {
+  const long long n = p.N * p.S;
+  k_dump<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, blob, lay);
+  return cudaGetLastError();
+}
+
+cudaError_t snk_launch_load(const Params& p, const u8* blob, const snk_state_layout& lay, cudaStream_t stream) {
+  const long long n = p.N * p.S;
+  k_load<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, blob, lay);
+  return cudaGetLastError();
+}
+
+cudaError_t snk_launch_gen_actions(int8_t* actions, long long N, int S, long long env_id_base, u64 step, u64 seed,
+                                   int n_actions, cudaStream_t stream) {
+  const long long n = N * S;
+  k_gen_actions<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(actions, N, S, env_id_base, step, seed, n_actions);
+  return cudaGetLastError();
+}

@@ -1,0 +1,23 @@
+// snk_launch.h -- host-visible launch interface between snk_api.cu and snk_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "../../include/snk.h"
+
+struct Params;
+
+struct LaunchPlan {
+  bool use_tile;    // k_step_tile (warp per env, TMA image store) or k_step_dense (CTA per env)
+  int grid, block;
+  size_t smem;
+  int occupancy;    // resident CTAs per SM
+  int max_grid;     // SMs * occupancy: persistent grid size
+};
+
+cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm);
+cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, cudaStream_t stream);
+cudaError_t snk_launch_dump(const Params& p, uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);
+cudaError_t snk_launch_load(const Params& p, const uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);
+cudaError_t snk_launch_gen_actions(int8_t* actions, long long N, int S, long long env_id_base, uint64_t step,
+                                   uint64_t seed, int n_actions, cudaStream_t stream);

@@ -1,0 +1,314 @@
+"""SnakeVecEnv -- the reference's VecEnv protocol over the CUDA library.
+
+Drop-in for what `utils.make_basic_env` returns in the reference (src/utils.py:34-49):
+a `SubprocVecEnv` (src/baselines/common/vec_env/subproc_vec_env.py:31) of
+`Monitor(SnakeEnv)` instances.  Same attributes and methods -- `num_envs`,
+`observation_space`, `action_space`, `reset()`, `step_async()`, `step_wait()`, `step()`,
+`close()` (src/baselines/common/vec_env/__init__.py:22-88) -- but all N envs live in HBM and
+one fused kernel steps them.  Observations, rewards and dones are returned as CUDA tensors that
+alias the library's buffers (no copy, no host round trip); `host_io=True` returns numpy arrays
+exactly like SubprocVecEnv.step_wait (`:57-61`).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .spaces import Box, Discrete
+
+
+class _DevPtr(object):
+    """A raw device pointer presented through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _alias(ptr, shape, typestr, device):
+    return torch.as_tensor(_DevPtr(ptr, shape, typestr), device=device)
+
+
+class Infos(object):
+    """Lazily materialised `infos` of one step: behaves like the tuple of per-env dicts that
+    SubprocVecEnv returns ({'ale.lives': 1, 'num_snakes': n[, 'episode': {'r','l','t'}]},
+    snake_multiple_test.py:197 + monitor.py:62-76) but only touches the host when indexed."""
+
+    def __init__(self, num_alive, done, ep_ret, ep_len, elapsed):
+        self._dev = (num_alive, done, ep_ret, ep_len)
+        self._host = None
+        self._elapsed = elapsed
+        self._n = int(done.shape[0])
+
+    def _fetch(self):
+        if self._host is None:
+            self._host = tuple(np.asarray(x.cpu() if isinstance(x, torch.Tensor) else x) for x in self._dev)
+        return self._host
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        alive, done, ret, length = self._fetch()
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        info = {"ale.lives": 1, "num_snakes": int(alive[i])}
+        if done[i]:
+            info["episode"] = {"r": round(float(ret[i]), 6), "l": int(length[i]), "t": self._elapsed}
+        return info
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+    def episodes(self):
+        """[{'r','l','t'}] of the envs that finished this step (what Runner.run collects,
+        ppo_multi_agent_new.py:189-192) without building N dicts."""
+        _, done, ret, length = self._fetch()
+        idx = np.flatnonzero(done)
+        return [{"r": round(float(ret[i]), 6), "l": int(length[i]), "t": self._elapsed} for i in idx]
+
+
+class SnakeVecEnv(object):
+    """N multi-snake envs stepped in lockstep on one GPU.
+
+    kwargs follow NewMultipleSnakes.__init__ (gym_snake/envs/snake_multiple_env_new.py:10):
+    `size`, `n_snakes`, `n_fruits`, `screen_res` (accepted, unused: no pyglet viewer), plus the
+    batch / device ones: `num_envs`, `rules` ('classic' | 'adversarial' | 'cut'), `n_views`
+    (K; the reference's SnakeEnv emits 3, snake_multiple_test.py:93-95), `seed`, `device`,
+    `env_id_base` (global id of env 0: shard offset under multi-GPU), `auto_reset`.
+    """
+
+    def __init__(self, num_envs, size=(10, 10), n_snakes=2, n_fruits=None, n_views=None, rules="classic",
+                 seed=0, device=0, env_id_base=0, auto_reset=True, max_steps=2000, screen_res=300, host_io=False):
+        import time
+        self._L = _lib.lib()
+        if isinstance(device, torch.device):
+            device = device.index or 0
+        elif isinstance(device, str):
+            device = torch.device(device).index or 0
+        self.cfg = _lib.make_config(num_envs, size, n_snakes, n_fruits, n_views, rules, max_steps, auto_reset,
+                                    device=device, env_id_base=env_id_base, seed=seed)
+        self.device = torch.device("cuda", self.cfg.device)
+        torch.cuda.init()
+        h = C.c_void_p()
+        _lib.check(self._L.snk_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+        self.lay = _lib.SnkStateLayout()
+        _lib.check(self._L.snk_state_layout_of(C.byref(self.cfg), C.byref(self.lay)))
+        self.num_envs = self.N = self.cfg.num_envs
+        self.S, self.F, self.K, self.D = self.cfg.n_snakes, self.cfg.n_fruits, self.cfg.n_views, self.cfg.size
+        self.V = self.D + 2
+        self.rules = rules
+        self.screen_res = screen_res
+        self.host_io = host_io
+        self.action_space = Discrete(6 if self.cfg.rules == _lib.RULES["cut"] else 5)
+        self.observation_space = Box(0, 255, (self.V, self.V, 3 * self.K), np.uint8)
+        self._bind_buffers()
+        self._actions = torch.zeros((self.N, self.S), dtype=torch.int8, device=self.device)
+        self._pending = False
+        self._tstart = time.time()
+        self._time = time
+        self.closed = False
+        if host_io:
+            self._h_actions = torch.zeros((self.N, self.S), dtype=torch.int8).pin_memory()
+            self._h_obs = torch.zeros(tuple(self.obs.shape), dtype=torch.uint8).pin_memory()
+            self._h_reward = torch.zeros(self.N, dtype=torch.float32).pin_memory()
+            self._h_done = torch.zeros(self.N, dtype=torch.uint8).pin_memory()
+            self._h_alive = torch.zeros(self.N, dtype=torch.uint8).pin_memory()
+
+    def _bind_buffers(self):
+        b = _lib.SnkBuffers()
+        _lib.check(self._L.snk_get_buffers(self._h, C.byref(b)))
+        N, S, dev = self.N, self.S, self.device
+        self.obs = _alias(b.d_obs, (N, b.obs_h, b.obs_w, b.obs_c), "|u1", dev)
+        self.rewards = _alias(b.d_reward, (N,), "<f4", dev)
+        self.rewards_all = _alias(b.d_reward_all, (N, S), "<f4", dev)
+        self._done_u8 = _alias(b.d_done, (N,), "|u1", dev)
+        self.num_alive = _alias(b.d_num_alive, (N,), "|u1", dev)
+        self.episode_return = _alias(b.d_episode_return, (N,), "<f4", dev)
+        self.episode_len = _alias(b.d_episode_len, (N,), "<i4", dev)
+        self._stats = _alias(b.d_stats, (_lib.NSTATS,), "<f8", dev)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ VecEnv protocol
+    def seed(self, seed=None):
+        """env.seed(seed + rank) of utils.py:39: re-keys the counter-based RNG.  Takes effect on a
+        fresh handle, so it is only allowed before the first reset."""
+        if seed is None:
+            return [int(self.cfg.seed)]
+        state = self.dump_state()
+        fresh = not state["t"].any() and not state["len"].any()
+        if not fresh:
+            raise _lib.SnkError("seed() must be called before the first reset()")
+        self.close()
+        self.__init__(self.N, self.D, self.S, self.F, self.K, self.rules, seed, self.cfg.device, self.cfg.env_id_base,
+                      bool(self.cfg.auto_reset), self.cfg.max_steps, self.screen_res, self.host_io)
+        return [int(seed)]
+
+    def reset(self, mask=None):
+        """VecEnv.reset (subproc_vec_env.py:63-66).  `mask` (bool [N], optional extension) resets a subset."""
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        _lib.check(self._L.snk_reset(self._h, C.c_void_p(m.data_ptr()) if m is not None else None, self._stream()))
+        if self.host_io:
+            return self.obs.cpu().numpy()
+        return self.obs
+
+    def step_async(self, actions):
+        """actions: [N][S] ints -- a CUDA int8 tensor is used as is; sequences of tuples (what
+        MultiModel.multi_step builds, ppo_multi_agent_new.py:35-37) and numpy arrays are copied."""
+        if self._pending:
+            raise _lib.SnkError("already running an async step")
+        if self.host_io:
+            self._h_actions.copy_(torch.as_tensor(np.asarray(actions).reshape(self.N, self.S)).to(torch.int8))
+        else:
+            if isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.int8 and actions.is_contiguous():
+                a = actions.view(self.N, self.S)
+            else:
+                a = torch.as_tensor(np.asarray(actions) if not isinstance(actions, torch.Tensor) else actions)
+                self._actions.copy_(a.reshape(self.N, self.S).to(torch.int8), non_blocking=True)
+                a = self._actions
+            self._a_live = a  # keep alive until step_wait
+            _lib.check(self._L.snk_step(self._h, C.c_void_p(a.data_ptr()), self._stream()))
+        self._pending = True
+
+    def step_wait(self):
+        if not self._pending:
+            raise _lib.SnkError("not running an async step")
+        self._pending = False
+        elapsed = round(self._time.time() - self._tstart, 6)
+        if self.host_io:
+            _lib.check(self._L.snk_step_host(
+                self._h, C.c_void_p(self._h_actions.data_ptr()), C.c_void_p(self._h_obs.data_ptr()),
+                C.c_void_p(self._h_reward.data_ptr()), C.c_void_p(self._h_done.data_ptr()),
+                C.c_void_p(self._h_alive.data_ptr()), self._stream()))
+            done = self._h_done.numpy().astype(bool)
+            infos = Infos(self._h_alive.numpy(), done, self.episode_return, self.episode_len, elapsed)
+            return self._h_obs.numpy(), self._h_reward.numpy(), done, infos
+        dones = self._done_u8.view(torch.bool)
+        return self.obs, self.rewards, dones, Infos(self.num_alive, self._done_u8, self.episode_return, self.episode_len, elapsed)
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        if not self.closed and getattr(self, "_h", None):
+            torch.cuda.synchronize(self.device)
+            self._L.snk_destroy(self._h)
+            self._h = None
+        self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, mode="rgb_array"):
+        """World view of env 0 (get_ob_world, snake_multiple_test.py:60-81): view 0 of the observation."""
+        if mode != "rgb_array":
+            raise NotImplementedError("only mode='rgb_array' (there is no pyglet viewer on a GPU box)")
+        return self.obs[0, :, :, 0:3].cpu().numpy()
+
+    @property
+    def unwrapped(self):
+        return self
+
+    # ------------------------------------------------------------------ extensions
+    def set_obs_target(self, tensor):
+        """Write observations straight into `tensor` (e.g. rollout[t], ppo_multi_agent_new.py:181)."""
+        if tensor is None:
+            _lib.check(self._L.snk_set_obs_target(self._h, None, 0))
+        else:
+            assert tensor.is_cuda and tensor.dtype == torch.uint8 and tensor.is_contiguous()
+            _lib.check(self._L.snk_set_obs_target(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel()))
+        self._bind_buffers()
+
+    def set_draw_tape(self, vals, bounds, offsets):
+        """Replay mode: recorded reference draws, CSR per env (parity tests)."""
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        assert len(offsets) == self.N + 1
+        b = None if bounds is None else np.ascontiguousarray(bounds, dtype=np.uint32)
+        _lib.check(self._L.snk_set_draw_tape(self._h, vals.ctypes.data_as(C.c_void_p),
+                                             None if b is None else b.ctypes.data_as(C.c_void_p),
+                                             offsets.ctypes.data_as(C.c_void_p)))
+
+    def dump_state_blob(self):
+        blob = np.zeros(self.lay.total_bytes, dtype=np.uint8)
+        _lib.check(self._L.snk_dump_state(self._h, blob.ctypes.data_as(C.c_void_p), blob.nbytes))
+        return blob
+
+    def load_state_blob(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        _lib.check(self._L.snk_load_state(self._h, blob.ctypes.data_as(C.c_void_p), blob.nbytes))
+
+    def dump_state(self):
+        return split_state(self.dump_state_blob(), self.lay, self.cfg)
+
+    def gen_actions(self, step, seed=1, out=None):
+        """Synthetic uniform action stream (Philox key (seed, global env id)), generated on device."""
+        out = self._actions if out is None else out
+        _lib.check(self._L.snk_gen_actions(self._h, C.c_void_p(out.data_ptr()), int(step), int(seed),
+                                           self.action_space.n, self._stream()))
+        return out
+
+    def stats(self, reduce=True):
+        """Running episode statistics (Monitor's aggregate role).  With torch.distributed
+        initialised and reduce=True the 8 doubles are summed over all ranks (NCCL all-reduce):
+        the only inter-GPU traffic of the env."""
+        s = self._stats.clone()
+        if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(s)
+        return dict(zip(_lib.STAT_NAMES, s.cpu().tolist()))
+
+    def reset_stats(self):
+        _lib.check(self._L.snk_reset_stats(self._h, self._stream()))
+
+    def check_errors(self):
+        flags = C.c_uint32(0)
+        _lib.check(self._L.snk_check_errors(self._h, C.byref(flags), self._stream()))
+        if flags.value:
+            raise _lib.SnkError("device error flags: " + ", ".join(v for k, v in _lib.DEVERR.items() if flags.value & k))
+
+    def launch_count(self):
+        n = C.c_uint64(0)
+        _lib.check(self._L.snk_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def launch_info(self):
+        out = (C.c_int32 * 6)()
+        _lib.check(self._L.snk_launch_info(self._h, out))
+        return dict(zip(("use_tile", "grid", "block", "smem", "occupancy", "envs_per_cta"), list(out)))
+
+    def algorithmic_bytes_per_step(self, mean_sum_len):
+        out = C.c_double(0)
+        _lib.check(self._L.snk_algorithmic_bytes_per_step(C.byref(self.cfg), float(mean_sum_len), C.byref(out)))
+        return out.value
+
+
+def split_state(blob, lay, cfg):
+    """Named numpy views of a canonical state blob (snk_state_layout, include/snk.h)."""
+    N, S, F, V = cfg.num_envs, cfg.n_snakes, cfg.n_fruits, cfg.size + 2
+    b = np.frombuffer(blob, dtype=np.uint8)
+
+    def arr(off, dtype, shape):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return b[off:off + n].view(dtype).reshape(shape)
+
+    out = {"t": arr(lay.off_t, np.int32, (N,)), "spare": arr(lay.off_spare, np.uint32, (N,)),
+           "draw_ctr": arr(lay.off_draw_ctr, np.uint32, (N,)), "ep_ret": arr(lay.off_ep_ret, np.float32, (N,)),
+           "ep_len": arr(lay.off_ep_len, np.int32, (N,)), "len": arr(lay.off_len, np.uint16, (N, S)),
+           "grow_to": arr(lay.off_grow_to, np.uint16, (N, S)), "vel": arr(lay.off_vel, np.uint8, (N, S)),
+           "body": arr(lay.off_body, np.uint16, (N, S, lay.cap))}
+    if lay.fruit_is_grid:
+        out["fruit_grid"] = arr(lay.off_fruit, np.uint8, (N, V * V))
+    else:
+        out["fruit"] = arr(lay.off_fruit, np.uint16, (N, F))
+    return out

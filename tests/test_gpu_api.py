@@ -1,0 +1,139 @@
+"""GPU: the Gym / VecEnv surface (shapes, dtypes, auto-reset contract, infos, host I/O, obs target)."""
+import numpy as np
+import pytest
+
+import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import snakes_b200
+    return snakes_b200
+
+
+def test_vecenv_surface(sb):
+    import torch
+    env = sb.make_basic_env("snake-multiple-test-v0", 64, seed=0)
+    assert env.num_envs == 64 and env.action_space.n == 5
+    assert env.observation_space.shape == (21, 21, 9) and env.observation_space.dtype == np.uint8
+    obs = env.reset()
+    assert obs.shape == (64, 21, 21, 9) and obs.dtype == torch.uint8 and obs.is_cuda
+    # list-of-tuples actions, as MultiModel.multi_step builds them (ppo_multi_agent_new.py:35-37)
+    actions = list(zip([1] * 64, [2] * 64))
+    env.step_async(actions)
+    with pytest.raises(sb.SnkError):
+        env.step_async(actions)
+    obs, rews, dones, infos = env.step_wait()
+    with pytest.raises(sb.SnkError):
+        env.step_wait()
+    assert rews.shape == (64,) and rews.dtype == torch.float32
+    assert dones.shape == (64,) and dones.dtype == torch.bool
+    assert len(infos) == 64 and infos[0]["ale.lives"] == 1 and "num_snakes" in infos[0]
+    # main view / opponent view slicing used by the learner (ppo_multi_agent_new.py:161-165)
+    assert obs[:, :, :, 0:3].shape == (64, 21, 21, 3)
+    env.close()
+
+
+def test_auto_reset_contract_and_episode_info(sb):
+    """subproc_vec_env.py:13-16: on done the env resets at once; obs is the first obs of the new
+    episode while reward/done/info belong to the terminal step; Monitor adds info['episode']."""
+    N = 256
+    env = sb.SnakeVecEnv(N, size=10, n_snakes=2, seed=3)
+    env.reset()
+    seen = 0
+    for t in range(60):
+        obs, rews, dones, infos = env.step(env.gen_actions(t, 2))
+        st = env.dump_state()
+        d = dones.cpu().numpy()
+        assert (st["t"][d] == 0).all() and (st["ep_len"][d] == 0).all()  # already reset
+        assert (st["len"][d] == 1).all()
+        eps = infos.episodes()
+        assert len(eps) == d.sum()
+        for i in np.flatnonzero(d)[:4]:
+            info = infos[int(i)]
+            assert info["episode"]["l"] >= 1 and info["episode"]["r"] >= -1.0
+            seen += 1
+        for i in np.flatnonzero(~d)[:2]:
+            assert "episode" not in infos[int(i)]
+    assert seen > 10
+    s = env.stats()
+    assert s["env_steps"] == 60 * N and s["episodes"] > 0 and s["length_sum"] > 0
+    env.close()
+
+
+def test_host_io_matches_device_path(sb):
+    """snk_step_host (numpy in / numpy out, like SubprocVecEnv.step_wait) == device path."""
+    kw = dict(size=10, n_snakes=2, seed=9)
+    dev = sb.SnakeVecEnv(128, **kw)
+    host = sb.SnakeVecEnv(128, host_io=True, **kw)
+    o1, o2 = dev.reset(), host.reset()
+    assert isinstance(o2, np.ndarray) and np.array_equal(o1.cpu().numpy(), o2)
+    for t in range(50):
+        a = dev.gen_actions(t, 7).cpu().numpy()
+        od, rd, dd, _ = dev.step(a)
+        oh, rh, dh, ih = host.step(a)
+        assert isinstance(oh, np.ndarray) and oh.dtype == np.uint8 and rh.dtype == np.float32 and dh.dtype == bool
+        assert np.array_equal(od.cpu().numpy(), oh) and np.array_equal(rd.cpu().numpy(), rh) and np.array_equal(dd.cpu().numpy(), dh)
+        assert ih[0]["num_snakes"] == int(dev.num_alive[0])
+    dev.close(); host.close()
+
+
+def test_obs_target_rollout_slot(sb):
+    """Observations written straight into a slot of a caller-owned rollout buffer."""
+    import torch
+    N = 96
+    env = sb.SnakeVecEnv(N, size=10, n_snakes=2, seed=1)
+    ref = sb.SnakeVecEnv(N, size=10, n_snakes=2, seed=1)
+    rollout = torch.zeros((4, N, 12, 12, 6), dtype=torch.uint8, device=env.device)
+    env.set_obs_target(rollout[0]); env.reset(); ref.reset()
+    assert torch.equal(rollout[0], ref.obs)
+    for t in range(3):
+        env.set_obs_target(rollout[t + 1])
+        a = ref.gen_actions(t, 3)
+        env.step(a); ref.step(a)
+        assert torch.equal(rollout[t + 1], ref.obs)
+    env.close(); ref.close()
+
+
+def test_single_env_gym_api(sb):
+    """gym.make(id) -> reset/step/seed like evaluate_snake.py:52-117 (no auto-reset, numpy out)."""
+    env = sb.make("snake-multiple-test-v0")
+    env.seed(5)
+    ob = env.reset()
+    assert isinstance(ob, np.ndarray) and ob.shape == (21, 21, 9) and ob.dtype == np.uint8
+    co = c_oracle.COracle(1, size=19, n_snakes=2, n_views=3, seed=5, auto_reset=False)
+    assert np.array_equal(co.reset()[0], ob)
+    done = False
+    steps = 0
+    rng = np.random.RandomState(0)
+    while not done and steps < 500:
+        a = rng.randint(0, 5, size=2)
+        ob, r, done, info = env.step(a)
+        cob, cr, cd, ci = co.step(a[None])
+        assert np.array_equal(ob, cob[0]) and r == float(cr[0]) and done == bool(cd[0])
+        assert isinstance(r, float) and isinstance(done, bool) and info["ale.lives"] == 1
+        steps += 1
+    assert done
+    ob2 = env.reset()
+    assert np.array_equal(ob2, co.reset()[0])
+    # kwargs through a second __init__ call, as utils.py:38 does
+    env.__init__(n_snakes=3, n_fruits=3)
+    assert env.reset().shape == (12, 12, 9)
+    assert env.step(1)[0].shape == (12, 12, 9)  # scalar action is wrapped (snake_multiple_test.py:167-168)
+    env.close()
+    for env_id in sb.ENV_IDS:
+        e = sb.make(env_id)
+        e.reset(); e.step([0] * e.n_snakes); e.close()
+
+
+def test_create_rejects_bad_config(sb):
+    with pytest.raises(sb.SnkError):
+        sb.SnakeVecEnv(4, size=1)
+    with pytest.raises(sb.SnkError):
+        sb.SnakeVecEnv(4, n_snakes=40)
+    with pytest.raises(ValueError):
+        sb.SnakeVecEnv(4, size=(10, 12))
+    with pytest.raises(ValueError):
+        sb.SnakeVecEnv(4, rules="nope")
