@@ -263,9 +263,10 @@ class SnakeVecEnv(object):
         """Running episode statistics (Monitor's aggregate role).  With torch.distributed
         initialised and reduce=True the 8 doubles are summed over all ranks (NCCL all-reduce):
         the only inter-GPU traffic of the env."""
+        from .sharding import all_reduce_stats
         s = self._stats.clone()
-        if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-            torch.distributed.all_reduce(s)
+        if reduce:
+            all_reduce_stats(s)
         return dict(zip(_lib.STAT_NAMES, s.cpu().tolist()))
 
     def reset_stats(self):
