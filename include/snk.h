@@ -43,6 +43,7 @@ extern "C" {
 #define SNK_DEVERR_TAPE_BOUND 2u      /* replayed draw was recorded with another bound */
 #define SNK_DEVERR_FRUIT_OVERFLOW 4u  /* >255 fruits on one cell (adversarial / cut grid) */
 #define SNK_DEVERR_BODY_OVERFLOW 8u   /* ring capacity exceeded (cannot happen for cap = D*D+1) */
+#define SNK_DEVERR_BAD_STATE 16u      /* snk_load_state: a body whose consecutive segments are not adjacent cells */
 
 /* rule-sets */
 #define SNK_RULES_CLASSIC 0      /* gym_snake/envs/snake_multiple_test.py  (SnakeEnv) */

@@ -76,11 +76,13 @@ static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 void so_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
 
 static uint32_t philox_bounded(uint64_t seed, uint64_t env_id, uint32_t stream, uint64_t index, uint32_t n) {
-  uint32_t ctr[4] = {(uint32_t)index, (uint32_t)(index >> 32), stream, (uint32_t)(seed >> 32)};
+  /* one Philox block (counter = index >> 2) serves four consecutive draws (word = index & 3) */
+  uint64_t blk = index >> 2;
+  uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), stream, (uint32_t)(seed >> 32)};
   uint32_t key[2] = {(uint32_t)seed, (uint32_t)env_id};
   uint32_t out[4];
   philox4x32_10(ctr, key, out);
-  return (uint32_t)(((uint64_t)out[0] * n) >> 32);
+  return (uint32_t)(((uint64_t)out[index & 3] * n) >> 32);
 }
 
 static uint32_t so_draw(so_vec* v, int64_t e, uint32_t n) {

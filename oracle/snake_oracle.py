@@ -89,8 +89,10 @@ STREAM_ENV, STREAM_ACTION = 0, 1
 
 
 def philox_bounded(seed, env_id, stream, index, n):
-    """Draw `index` of (seed, env_id, stream) mapped to [0, n) by hi32(u32 * n)."""
-    x = philox4x32_10((index & _U32, (index >> 32) & _U32, stream, (seed >> 32) & _U32), (seed & _U32, env_id & _U32))[0]
+    """Draw `index` of (seed, env_id, stream) mapped to [0, n) by hi32(u32 * n).  One Philox block
+    (counter = index >> 2) serves four consecutive draws (word = index & 3)."""
+    blk = index >> 2
+    x = philox4x32_10((blk & _U32, (blk >> 32) & _U32, stream, (seed >> 32) & _U32), (seed & _U32, env_id & _U32))[index & 3]
     return (x * n) >> 32
 
 

@@ -149,14 +149,33 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   p.max_steps = h->cfg.max_steps; p.auto_reset = cfg->auto_reset != 0; p.rng_mode = cfg->rng_mode;
   p.N = N; p.env_id_base = cfg->env_id_base; p.seed = cfg->seed;
 
-  // launch plan: tile kernel when W observations + template + scratch leave room for >= 2 CTAs per SM
+  // launch plan.  lane kernel (chain-coded bodies, lane per env) for small boards; otherwise the
+  // warp-per-env tile kernel while W observations + template + scratch leave room for >= 2 CTAs per
+  // SM; otherwise the CTA-per-env dense kernel.
   LaunchPlan& plan = h->plan;
+  const char* force = getenv("SNK_FORCE_KERNEL");  // "lane" | "tile" | "dense": testing aid
+  int TE = 0;
+  if (S <= 4 && F <= 4 && D <= 32 && K <= 8) {
+    const int cand[3] = {32, 16, 8};
+    for (int i = 0; i < 3 && !TE; ++i)
+      if (cand[i] % p.G == 0 && (size_t)cand[i] * p.E <= 28 * 1024) TE = cand[i];
+    if (!TE && p.G <= 8 && (size_t)8 * p.E <= 48 * 1024) TE = 8;
+  }
   const int W = p.G > 8 ? p.G : 8;
-  const size_t smem_tile = (size_t)(W + p.G) * p.E + (size_t)W * (p.RW + p.bm_words) * 4;
-  const char* force = getenv("SNK_FORCE_KERNEL");  // "dense" or "tile": testing aid
-  plan.use_tile = smem_tile <= 110 * 1024;
-  if (force && !strcmp(force, "dense")) plan.use_tile = false;
-  if (plan.use_tile) {
+  const size_t smem_tile = (size_t)(W + p.G) * p.E + (size_t)W * (REC_SNAKE0 + 2 * S + (F + 1) / 2 + 3 + p.bm_words) * 4;
+  plan.kind = TE ? KIND_LANE : smem_tile <= 110 * 1024 ? KIND_TILE : KIND_DENSE;
+  if (force && !strcmp(force, "dense")) plan.kind = KIND_DENSE;
+  if (force && !strcmp(force, "tile") && smem_tile <= 200 * 1024) plan.kind = KIND_TILE;
+  if (force && !strcmp(force, "lane") && !TE) { snk_destroy(h); return fail(SNK_EINVAL, "lane kernel does not support this configuration"); }
+  p.family = plan.kind == KIND_LANE;
+  p.CW = (p.cap - 1 + 15) / 16;
+  if (plan.kind == KIND_LANE) {
+    p.RW = (REC_SNAKE0 + 2 * S + 2 + 3) & ~3;
+    p.TE = TE; p.W = 32;
+    p.tile_stride = (int)(((size_t)TE * p.E + 127) & ~(size_t)127);
+    plan.block = 64; plan.smem = (size_t)2 * p.tile_stride;
+    p.n_groups = (N + 31) / 32;
+  } else if (plan.kind == KIND_TILE) {
     p.W = W; plan.block = 32 * W; plan.smem = smem_tile;
     p.n_groups = (N + W - 1) / W;
   } else {
@@ -164,12 +183,17 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     p.n_groups = N;
     if (plan.smem > 200 * 1024) { snk_destroy(h); return fail(SNK_EINVAL, "board too large for shared memory"); }
   }
-  CUDA_TRY_H(snk_plan(cfg->rules, plan, h->n_sm));
-  plan.grid = (int)(p.n_groups < plan.max_grid ? p.n_groups : plan.max_grid);
+  CUDA_TRY_H(snk_plan(cfg->rules, plan, h->n_sm, S));
+  {
+    const long long work = plan.kind == KIND_LANE ? (p.n_groups + 1) / 2 : p.n_groups;  // lane: 2 warps per CTA
+    plan.grid = (int)(work < plan.max_grid ? work : plan.max_grid);
+    if (plan.grid < 1) plan.grid = 1;
+  }
 
   // device buffers
   TRY(dev_alloc(h, &p.rec, (size_t)N * p.RW, true));
-  TRY(dev_alloc(h, &p.body, (size_t)N * S * p.cap, true));
+  if (p.family == 1) TRY(dev_alloc(h, &p.chain, (size_t)N * S * p.CW, true));
+  else TRY(dev_alloc(h, &p.body, (size_t)N * S * p.cap, true));
   if (cfg->rules != SNK_RULES_CLASSIC) TRY(dev_alloc(h, &p.grid, (size_t)N * p.grid_stride, true));
   TRY(dev_alloc(h, &h->d_obs_own, (size_t)N * p.E, true));
   p.obs = h->d_obs_own;
@@ -378,9 +402,9 @@ extern "C" int snk_launch_count(const snk_handle* h, uint64_t* out) {
   return SNK_OK;
 }
 
-extern "C" int snk_launch_info(const snk_handle* h, int32_t* out /*[6]: use_tile, grid, block, smem, occupancy, W*/) {
+extern "C" int snk_launch_info(const snk_handle* h, int32_t* out /*[6]: kind, grid, block, smem, occupancy, envs per CTA*/) {
   if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
-  out[0] = h->plan.use_tile; out[1] = h->plan.grid; out[2] = h->plan.block; out[3] = (int32_t)h->plan.smem;
-  out[4] = h->plan.occupancy; out[5] = h->p.W;
+  out[0] = h->plan.kind; out[1] = h->plan.grid; out[2] = h->plan.block; out[3] = (int32_t)h->plan.smem;
+  out[4] = h->plan.occupancy; out[5] = h->plan.kind == KIND_LANE ? 64 : h->p.W;
   return SNK_OK;
 }

@@ -13,6 +13,7 @@
 // clearing, reward / done, Monitor accounting, in-place auto-reset and the RGB encoding of
 // all K views (reference: gym_snake/envs/snake_multiple_test.py:166-197 + :35-58 + :93-95).
 #include "snk_device.cuh"
+#include "snk_lane.cuh"
 #include "snk_launch.h"
 
 // ------------------------------------------------------------------ TMA bulk-copy wrappers
@@ -150,6 +151,94 @@ __global__ void __launch_bounds__(BLOCK) k_step_tile(const Params p) {
   if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
+
+// k_step_lane: see snk_lane.cuh.  A warp is an independent worker: 32 envs of logic (one per lane),
+// then 32/TE rounds of paint -> TMA bulk store -> un-paint on its private image.  No __syncthreads.
+template <int S, int RULES>
+__global__ void __launch_bounds__(64) k_step_lane(const Params p) {
+  extern __shared__ __align__(128) u8 smem[];
+  __shared__ double s_stats[SNK_NSTATS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
+  const int TE = p.TE, LPE = 32 / TE, E = p.E;
+  const int tile_bytes = TE * E;
+  u8* tile = smem + warp * p.tile_stride;
+  {  // border-only image of TE envs
+    const uint4* src = reinterpret_cast<const uint4*>(p.tmpl);
+    const int n16 = p.G * E / 16;
+    for (int c = 0; c < TE / p.G; ++c) {
+      uint4* dst = reinterpret_cast<uint4*>(tile + c * p.G * E);
+      for (int i = lane; i < n16; i += 32) dst[i] = src[i];
+    }
+  }
+  if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  __syncthreads();
+  LaneStats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  u32 errs = 0;
+  const int slot = lane / LPE, sub = lane - slot * LPE;
+  u8* img = tile + slot * E;
+  const long long n_batches = (p.N + 31) / 32;
+  for (long long b = (long long)blockIdx.x * wpc + warp; b < n_batches; b += (long long)gridDim.x * wpc) {
+    const long long e = b * 32 + lane;
+    const bool valid = e < p.N;
+    LaneEnv<S> env;
+#pragma unroll
+    for (int s = 0; s < S; ++s) { env.head[s] = 0; env.len[s] = 0; env.c0[s] = 0; env.grow[s] = 0; env.vel[s] = 0; }
+    env.fruit[0] = env.fruit[1] = env.fruit[2] = env.fruit[3] = 0;
+    if (valid) {
+      LaneRng rng;
+      rng.have = false; rng.blk = 0;
+      u8* grid = p.grid ? p.grid + e * p.grid_stride : nullptr;
+      lane_load<S>(p, e, env);
+      if (p.mode == MODE_STEP) {
+        lane_step<S, RULES>(p, e, env, rng, grid, errs, st);
+      } else if (p.mode == MODE_RESET) {
+        if (!p.mask || p.mask[e]) lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);
+      }
+      if (p.mode != MODE_OBSERVE) lane_store<S>(p, e, env);
+    }
+    __syncwarp();  // chain words / fruit grid written by the owner lane are read by the painting lanes
+    for (int q = 0; q < LPE; ++q) {
+      const long long e0 = b * 32 + (long long)q * TE;
+      if (e0 >= p.N) break;
+      const int owner = q * TE + slot;
+      lane_paint<S, RULES, true>(p, env, valid, e0 + slot, owner, sub, LPE, img);
+      fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
+      __syncwarp();
+      const long long left = p.N - e0;
+      u8* gdst = p.obs + e0 * (long long)E;
+      if (left >= TE) {
+        if (lane == 0) {
+          for (int off = 0; off < tile_bytes; off += 16384)
+            bulk_store_s2g(gdst + off, tile + off, (u32)min(16384, tile_bytes - off));
+          bulk_commit();
+          bulk_wait_read();  // the engine has read the image: it may be modified again
+        }
+      } else {  // last, partial image: plain stores for the valid envs only
+        const int bytes = (int)left * E;
+        for (int i = lane; i < bytes; i += 32) gdst[i] = tile[i];
+      }
+      __syncwarp();
+      lane_paint<S, RULES, false>(p, env, valid, e0 + slot, owner, sub, LPE, img);
+      __syncwarp();
+    }
+  }
+  if (lane == 0) bulk_wait_all();
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    st.steps += __shfl_xor_sync(FULL, st.steps, o); st.episodes += __shfl_xor_sync(FULL, st.episodes, o);
+    st.ret_sum += __shfl_xor_sync(FULL, st.ret_sum, o); st.len_sum += __shfl_xor_sync(FULL, st.len_sum, o);
+    st.fruits += __shfl_xor_sync(FULL, st.fruits, o); st.deaths += __shfl_xor_sync(FULL, st.deaths, o);
+    st.cells += __shfl_xor_sync(FULL, st.cells, o); st.draws += __shfl_xor_sync(FULL, st.draws, o);
+    errs |= __shfl_xor_sync(FULL, errs, o);
+  }
+  {
+    WarpStats ws = {st.steps, st.episodes, st.ret_sum, st.len_sum, st.fruits, st.deaths, st.cells, st.draws};
+    flush_stats(p, ws, errs, s_stats, lane);
+  }
+  __syncthreads();
+  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+}
+
 template <int RULES>
 __global__ void __launch_bounds__(256) k_step_dense(const Params p) {
   extern __shared__ __align__(128) u8 smem[];
@@ -219,8 +308,14 @@ __global__ void k_dump(const Params p, u8* blob, snk_state_layout lay) {
   reinterpret_cast<u16*>(blob + lay.off_grow_to)[i] = (u16)(b & 0xffff);
   (blob + lay.off_vel)[i] = (u8)(b >> 16);
   u16* dst = reinterpret_cast<u16*>(blob + lay.off_body) + i * cap;
-  const u16* ring = p.body + i * cap;
-  for (int k = 0; k < cap; ++k) dst[k] = k < len ? (u16)ring_at(ring, hs, k, cap) : (u16)0;
+  if (p.family == 1) {  // chain code: hs is the head id
+    const u32* ch = p.chain + i * p.CW;
+    for (int k = 0; k < cap; ++k) dst[k] = 0;
+    chain_walk(hs, len, ch[0], ch, p.V, [&](int k, int pid) { dst[k] = (u16)pid; });
+  } else {
+    const u16* ring = p.body + i * cap;
+    for (int k = 0; k < cap; ++k) dst[k] = k < len ? (u16)ring_at(ring, hs, k, cap) : (u16)0;
+  }
   if (s == 0) {
     reinterpret_cast<int32_t*>(blob + lay.off_t)[e] = (int32_t)r[REC_T];
     reinterpret_cast<u32*>(blob + lay.off_spare)[e] = r[REC_SPARE];
@@ -246,11 +341,23 @@ __global__ void k_load(const Params p, const u8* blob, snk_state_layout lay) {
   const u32 len = reinterpret_cast<const u16*>(blob + lay.off_len)[i];
   const u32 grow = reinterpret_cast<const u16*>(blob + lay.off_grow_to)[i];
   const u32 vel = (blob + lay.off_vel)[i];
-  r[REC_SNAKE0 + 2 * s] = 0u | (len << 16);
   r[REC_SNAKE0 + 2 * s + 1] = grow | (vel << 16);
   const u16* src = reinterpret_cast<const u16*>(blob + lay.off_body) + i * cap;
-  u16* ring = p.body + i * cap;
-  for (int k = 0; k < cap; ++k) ring[k] = src[k];
+  if (p.family == 1) {  // chain code: direction of segment k+1 -> k, 16 per word
+    r[REC_SNAKE0 + 2 * s] = (u32)src[0] | (len << 16);
+    u32* ch = p.chain + i * p.CW;
+    for (int k = 0; k < p.CW; ++k) ch[k] = 0;
+    for (int k = 0; k + 1 < (int)len; ++k) {
+      const int diff = (int)src[k] - (int)src[k + 1];
+      const u32 d = diff == p.V ? 0u : diff == 1 ? 1u : diff == -p.V ? 2u : diff == -1 ? 3u : 4u;
+      if (d == 4u) { atomicOr(p.err, SNK_DEVERR_BAD_STATE); break; }
+      ch[k >> 4] |= d << (2 * (k & 15));
+    }
+  } else {
+    r[REC_SNAKE0 + 2 * s] = 0u | (len << 16);
+    u16* ring = p.body + i * cap;
+    for (int k = 0; k < cap; ++k) ring[k] = src[k];
+  }
   if (s == 0) {
     r[REC_T] = (u32) reinterpret_cast<const int32_t*>(blob + lay.off_t)[e];
     r[REC_SPARE] = reinterpret_cast<const u32*>(blob + lay.off_spare)[e];
@@ -276,9 +383,23 @@ __global__ void k_gen_actions(int8_t* actions, long long N, int S, long long env
 }
 
 // ------------------------------------------------------------------ launchers
+template <int S, int RULES>
+static cudaError_t launch_lane(const Params& p, const LaunchPlan& plan, cudaStream_t stream) {
+  k_step_lane<S, RULES><<<plan.grid, plan.block, plan.smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
 template <int RULES>
 static cudaError_t launch_rules(const Params& p, const LaunchPlan& plan, cudaStream_t stream) {
-  if (plan.use_tile) {
+  if (plan.kind == KIND_LANE) {
+    switch (p.S) {
+      case 1: return launch_lane<1, RULES>(p, plan, stream);
+      case 2: return launch_lane<2, RULES>(p, plan, stream);
+      case 3: return launch_lane<3, RULES>(p, plan, stream);
+      default: return launch_lane<4, RULES>(p, plan, stream);
+    }
+  }
+  if (plan.kind == KIND_TILE) {
     if (plan.block <= 256) k_step_tile<RULES, 256><<<plan.grid, plan.block, plan.smem, stream>>>(p);
     else k_step_tile<RULES, 512><<<plan.grid, plan.block, plan.smem, stream>>>(p);
   } else {
@@ -295,14 +416,29 @@ cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, 
   }
 }
 
+template <int S, int RULES>
+static cudaError_t plan_lane(LaunchPlan& plan, int& occ) {
+  cudaError_t err;
+  if ((err = cudaFuncSetAttribute(k_step_lane<S, RULES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_lane<S, RULES>, plan.block, plan.smem);
+}
+
 template <int RULES>
-static cudaError_t plan_rules(LaunchPlan& plan, int n_sm) {
+static cudaError_t plan_rules(LaunchPlan& plan, int n_sm, int S) {
   cudaError_t err;
   int occ = 0;
-  if (plan.use_tile && plan.block <= 256) {
+  if (plan.kind == KIND_LANE) {
+    switch (S) {
+      case 1: err = plan_lane<1, RULES>(plan, occ); break;
+      case 2: err = plan_lane<2, RULES>(plan, occ); break;
+      case 3: err = plan_lane<3, RULES>(plan, occ); break;
+      default: err = plan_lane<4, RULES>(plan, occ); break;
+    }
+    if (err) return err;
+  } else if (plan.kind == KIND_TILE && plan.block <= 256) {
     if ((err = cudaFuncSetAttribute(k_step_tile<RULES, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
     if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_tile<RULES, 256>, plan.block, plan.smem))) return err;
-  } else if (plan.use_tile) {
+  } else if (plan.kind == KIND_TILE) {
     if ((err = cudaFuncSetAttribute(k_step_tile<RULES, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
     if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_tile<RULES, 512>, plan.block, plan.smem))) return err;
   } else {
@@ -315,11 +451,11 @@ static cudaError_t plan_rules(LaunchPlan& plan, int n_sm) {
   return cudaSuccess;
 }
 
-cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm) {
+cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm, int S) {
   switch (rules) {
-    case SNK_RULES_CLASSIC: return plan_rules<SNK_RULES_CLASSIC>(plan, n_sm);
-    case SNK_RULES_ADVERSARIAL: return plan_rules<SNK_RULES_ADVERSARIAL>(plan, n_sm);
-    default: return plan_rules<SNK_RULES_CUT>(plan, n_sm);
+    case SNK_RULES_CLASSIC: return plan_rules<SNK_RULES_CLASSIC>(plan, n_sm, S);
+    case SNK_RULES_ADVERSARIAL: return plan_rules<SNK_RULES_ADVERSARIAL>(plan, n_sm, S);
+    default: return plan_rules<SNK_RULES_CUT>(plan, n_sm, S);
   }
 }
 

@@ -1,0 +1,374 @@
+// snk_lane.cuh -- k_step_lane: the fast path for small boards (S <= 4, F <= 4, D <= 32).
+//
+// One LANE per env for the game logic, one WARP per batch of 32 consecutive envs, no CTA-wide
+// synchronisation.  Differences from the warp-per-env kernels (snk_kernels.cu), all driven by the
+// round-1 profile (944 warp-instructions per env-step, issue-bound at 24 % of the HBM roofline):
+//
+//  * body = chain code.  Consecutive segments are always adjacent cells, so a body is its head id
+//    plus 2 bits per further segment (direction of the move that created segment i from i+1).  The
+//    first 16 directions live in one register (one u32 in HBM); longer bodies spill to `chain`
+//    words.  Advancing = shift in 2 bits; popping the tail = len-1; walking = register ALU only.
+//  * the scalar logic of 32 envs runs in the 32 lanes at once (it ran 32x redundantly before).
+//  * each warp owns a shared-memory image of TE (8/16/32) observations holding the border; LPE =
+//    32/TE lanes paint one env by walking its chain (each lane owns fixed byte positions of a pixel,
+//    so the reference's paint order -- fruits, snakes by index -- is kept without barriers), lane 0
+//    hands the image to the TMA engine (cp.async.bulk.global.shared::cta), and after the engine has
+//    read it the same walk un-paints.  No template restore, no lists, any body length.
+//
+// Reference semantics: gym_snake/envs/snake_multiple_test.py (cited per block below),
+// snake_adversarial_env.py:137-141,180-186, subproc_vec_env.py:13-16, monitor.py:57-78.
+#pragma once
+#include "snk_device.cuh"
+
+template <int S>
+struct LaneRec {  // record words of the lane family: header 8, snakes 2S, room for 4 fruits
+  static constexpr int RW = (REC_SNAKE0 + 2 * S + 2 + 3) & ~3;
+};
+
+template <int S>
+struct LaneEnv {
+  u32 t, ep_len, ctr, spare;
+  float ep_ret;
+  int head[S], len[S], grow[S], vel[S];
+  u32 c0[S];
+  int fruit[4];
+};
+
+struct LaneRng {  // one cached Philox block: four consecutive draws cost one evaluation
+  u32 blk;
+  bool have;
+  Philox4 o;
+};
+
+__device__ __forceinline__ int chain_delta(u32 d, int V) {  // d = vel-1: +V, +1, -V, -1
+  const int dv = (d & 1) ? 1 : V;
+  return (d & 2) ? -dv : dv;
+}
+
+// visit(i, pid) for every segment, head first
+template <class Fn>
+__device__ __forceinline__ void chain_walk(int head, int len, u32 c0, const u32* __restrict__ ch, int V, Fn visit) {
+  int pid = head;
+  u32 w = c0;
+  for (int i = 0; i < len; ++i) {
+    visit(i, pid);
+    const int j = i & 15;
+    if (j == 0 && i) w = ch[i >> 4];
+    pid -= chain_delta((w >> (2 * j)) & 3, V);
+  }
+}
+
+template <int S>
+__device__ __forceinline__ u32 lane_draw(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, u32 n, u32& errs, float& draws) {
+  const u32 idx = env.ctr++;
+  draws += 1.f;
+  if (p.rng_mode == SNK_RNG_TAPE) {
+    const u64 pos = p.tape_off[e] + idx;
+    if (pos >= p.tape_off[e + 1]) { errs |= SNK_DEVERR_TAPE_UNDERRUN; return 0; }
+    if (p.tape_bounds && p.tape_bounds[pos] != n) errs |= SNK_DEVERR_TAPE_BOUND;
+    return p.tape_vals[pos];
+  }
+  const u32 blk = idx >> 2;
+  if (!rng.have || rng.blk != blk) {
+    rng.o = philox_block(blk, 0, 0, (u32)(p.seed >> 32), (u32)p.seed, (u32)(p.env_id_base + e));
+    rng.blk = blk; rng.have = true;
+  }
+  const u32 sel = idx & 3;
+  const u32 x = sel == 0 ? rng.o.w[0] : sel == 1 ? rng.o.w[1] : sel == 2 ? rng.o.w[2] : rng.o.w[3];
+  return __umulhi(x, n);
+}
+
+// safe_choose_cell (:202-217), one lane: bitmap of the y-major indices of every live body cell
+// (un-bounds-checked: cellinfo carries the aliased index of an out-of-board head), k-th free one.
+template <int S>
+__device__ __forceinline__ int lane_spawn(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, u32& errs, float& draws) {
+  u32 bm[32];
+  const int nW = p.bm_words, DD = p.D * p.D;
+  for (int w = 0; w < nW; ++w) bm[w] = 0;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    chain_walk(env.head[s], env.len[s], env.c0[s], p.chain + (e * S + s) * p.CW, p.V, [&](int, int pid) {
+      const u32 idx = __ldg(p.cellinfo + pid) & 0x7fffffffu;
+      if (idx < (u32)DD) bm[idx >> 5] |= 1u << (idx & 31);
+    });
+  }
+  int total = 0;
+  for (int w = 0; w < nW; ++w) {
+    u32 fr = ~bm[w];
+    if (w == nW - 1 && (DD & 31)) fr &= (1u << (DD & 31)) - 1;
+    bm[w] = fr;
+    total += __popc(fr);
+  }
+  if (total == 0) return p.V + 1;  // (0,0), no draw (:212-215)
+  int k = (int)lane_draw<S>(p, e, env, rng, (u32)total, errs, draws);
+  for (int w = 0; w < nW; ++w) {
+    const int c = __popc(bm[w]);
+    if (k < c) return p.idx2pid[w * 32 + (int)__fns(bm[w], 0, k + 1)];
+    k -= c;
+  }
+  return p.V + 1;
+}
+
+// reset (:219-232): snake_i.x, snake_i.y, fruit_i.x, fruit_i.y interleaved, randint(D) each
+template <int S, int RULES>
+__device__ __forceinline__ void lane_reset(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, u8* grid, u32& errs, float& draws) {
+  const int F = p.F, V = p.V;
+  if (RULES != SNK_RULES_CLASSIC) {
+    u32* g32 = reinterpret_cast<u32*>(grid);
+    for (int w = 0; w < p.grid_stride / 4; ++w) g32[w] = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < S) {
+      const int x = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
+      const int y = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
+      env.head[i < S ? i : 0] = (x + 1) * V + (y + 1);
+      env.len[i < S ? i : 0] = 1; env.grow[i < S ? i : 0] = 3; env.vel[i < S ? i : 0] = 0; env.c0[i < S ? i : 0] = 0;
+    }
+    if (i < F) {
+      const int x = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
+      const int y = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
+      const int pid = (x + 1) * V + (y + 1);
+      if (RULES == SNK_RULES_CLASSIC) env.fruit[i] = pid; else grid_inc(grid, pid, errs);
+    }
+  }
+  env.t = 0; env.ep_len = 0; env.ep_ret = 0.f;  // `spare` survives (snake_adversarial_env.py:14)
+}
+
+struct LaneStats {
+  float steps, episodes, ret_sum, len_sum, fruits, deaths, cells, draws;
+};
+
+// One env step in one lane (:166-197).
+template <int S, int RULES>
+__device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, u8* grid, u32& errs, LaneStats& st) {
+  const int V = p.V, F = p.F;
+  const u32* chain_e = p.chain + e * S * p.CW;
+  int act[S];
+  {
+    const int8_t* a = p.actions + e * S;
+#pragma unroll
+    for (int s = 0; s < S; ++s) act[s] = a[s];
+  }
+  u32 was_alive = 0, moved = 0, strike = 0;
+  int eaten[S];
+  // ---- update_snake for every snake in index order (:97-145)
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    eaten[s] = 0;
+    if (env.len[s] == 0) continue;
+    was_alive |= 1u << s;
+    const int a = act[s];
+    int vel = env.vel[s];
+    if (a >= 1 && a <= 4 && vel != (((a + 1) & 3) + 1)) vel = a;   // :108-115
+    if (RULES == SNK_RULES_CUT && a == 5) strike |= 1u << s;
+    if (vel == 0) continue;                                          // :119
+    const int head = env.head[s] + chain_delta((u32)(vel - 1), V);
+    int n_eat = 0;
+    u32 hitmask = 0;
+    if (RULES == SNK_RULES_CLASSIC) {
+#pragma unroll
+      for (int f = 0; f < 4; ++f) if (f < F && env.fruit[f] == head) { hitmask |= 1u << f; ++n_eat; }   // :126-132
+    } else {
+      n_eat = grid[head];
+    }
+    const int grow = env.grow[s] + 2 * n_eat;
+    int len = env.len[s];
+    if (len >= grow) len--;                                          // :134-135
+    len++;                                                           // :137
+    {  // push the new direction: segment 0 -> 1 was created by `vel`
+      u32* ch = p.chain + (e * S + s) * p.CW;
+      const int nw = (len - 1 + 15) >> 4;
+      u32 carry = env.c0[s] >> 30;
+      env.c0[s] = (env.c0[s] << 2) | (u32)(vel - 1);
+      for (int k = 1; k < nw; ++k) { const u32 w = ch[k]; ch[k] = (w << 2) | carry; carry = w >> 30; }
+    }
+    env.head[s] = head; env.len[s] = len; env.grow[s] = grow; env.vel[s] = vel;
+    if (RULES == SNK_RULES_CLASSIC) {
+      for (; hitmask; hitmask &= hitmask - 1) {                      // :139-140, half-updated world
+        const int f = __ffs(hitmask) - 1;
+        const int cell = lane_spawn<S>(p, e, env, rng, errs, st.draws);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) if (g == f) env.fruit[g] = cell;
+      }
+    } else {
+      for (int i = 0; i < n_eat; ++i) {
+        if (RULES == SNK_RULES_ADVERSARIAL && env.spare > 0) {       // snake_adversarial_env.py:138-139
+          env.spare--;
+        } else {
+          const int cell = lane_spawn<S>(p, e, env, rng, errs, st.draws);
+          grid[head]--; grid_inc(grid, cell, errs);
+        }
+      }
+    }
+    moved |= 1u << s;
+    eaten[s] = n_eat;
+  }
+  // ---- is_snake_alive for all snakes on the post-move bodies, before anything is cleared (:147-164, :178-182)
+  u32 empty = 0, oob = 0, hit_own = 0, hit_head = 0, hit_body = 0;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    if (env.len[s] == 0) empty |= 1u << s;
+    else if (__ldg(p.cellinfo + env.head[s]) >> 31) oob |= 1u << s;
+  }
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    chain_walk(env.head[j], env.len[j], env.c0[j], chain_e + j * p.CW, V, [&](int i, int pid) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (env.len[s] && pid == env.head[s]) {
+          if (i == 0) { if (j != s) hit_head |= 1u << s; }
+          else if (j == s) hit_own |= 1u << s;
+          else hit_body |= 1u << s;
+        }
+      }
+    });
+  }
+  u32 dead = empty | oob | hit_own | hit_head | hit_body;
+  if (RULES == SNK_RULES_CUT) {
+    const u32 saved = strike & moved & hit_body & ~(empty | oob | hit_own | hit_head);
+    dead &= ~saved;
+    if (saved) {
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        int cut = 0x7fffffff;
+        chain_walk(env.head[j], env.len[j], env.c0[j], chain_e + j * p.CW, V, [&](int i, int pid) {
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            if (s != j && ((saved >> s) & 1) && i >= 1 && pid == env.head[s] && i < cut) cut = i;
+        });
+        if (cut < env.len[j]) {
+          chain_walk(env.head[j], env.len[j], env.c0[j], chain_e + j * p.CW, V, [&](int i, int pid) {
+            if (i < cut) return;
+            bool under = false;
+#pragma unroll
+            for (int s = 0; s < S; ++s) under |= ((saved >> s) & 1) && pid == env.head[s];
+            if (!under) grid_inc(grid, pid, errs);
+          });
+          env.len[j] = cut; env.grow[j] = cut;
+        }
+      }
+    }
+  }
+  if (RULES == SNK_RULES_ADVERSARIAL) {  // snake_adversarial_env.py:180-186
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      if (!((dead & ~empty) >> j & 1)) continue;
+      chain_walk(env.head[j], env.len[j], env.c0[j], chain_e + j * p.CW, V, [&](int, int pid) { grid_inc(grid, pid, errs); });
+      env.spare += (u32)(env.len[j] * env.len[j]);
+    }
+  }
+  // ---- clear (:184-185), reward (:187-190), t (:192-193), done (:195), Monitor (monitor.py:57-78)
+  int cells = 0;
+#pragma unroll
+  for (int s = 0; s < S; ++s) { if ((dead >> s) & 1) env.len[s] = 0; cells += env.len[s]; }
+  const bool main_dead = dead & 1u;
+  const float r0 = main_dead ? -1.f : (float)eaten[0];
+  env.t += 1;
+  const bool done = env.t >= (u32)p.max_steps || main_dead;
+  env.ep_ret += r0;
+  env.ep_len += 1;
+  int fruits = 0;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const bool d = (dead >> s) & 1;
+    const float r = s == 0 ? r0 : d ? (((was_alive >> s) & 1) ? -1.f : 0.f) : (float)eaten[s];
+    p.reward_all[e * S + s] = r;
+    fruits += eaten[s];
+  }
+  p.reward[e] = r0;
+  p.done[e] = done;
+  p.num_alive[e] = (u8)(S - __popc(dead));
+  p.fin_ret[e] = done ? env.ep_ret : 0.f;
+  p.fin_len[e] = done ? (int)env.ep_len : 0;
+  st.steps += 1.f;
+  st.fruits += (float)fruits;
+  st.deaths += (float)__popc(dead & was_alive);
+  st.cells += (float)cells;
+  if (done) {
+    st.episodes += 1.f; st.ret_sum += env.ep_ret; st.len_sum += (float)env.ep_len;
+    if (p.auto_reset) lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);  // subproc_vec_env.py:13-16
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void lane_load(const Params& p, long long e, LaneEnv<S>& env) {
+  constexpr int RW = LaneRec<S>::RW;
+  u32 r[RW];
+  const uint4* g = reinterpret_cast<const uint4*>(p.rec + e * RW);
+#pragma unroll
+  for (int i = 0; i < RW / 4; ++i) { const uint4 v = g[i]; r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w; }
+  env.t = r[REC_T]; env.ep_len = r[REC_EP_LEN]; env.ctr = r[REC_DRAW_CTR]; env.ep_ret = __uint_as_float(r[REC_EP_RET]);
+  env.spare = r[REC_SPARE];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    env.head[s] = r[REC_SNAKE0 + 2 * s] & 0xffff; env.len[s] = r[REC_SNAKE0 + 2 * s] >> 16;
+    env.grow[s] = r[REC_SNAKE0 + 2 * s + 1] & 0xffff; env.vel[s] = r[REC_SNAKE0 + 2 * s + 1] >> 16;
+    env.c0[s] = p.chain[(e * S + s) * p.CW];
+  }
+  env.fruit[0] = r[REC_SNAKE0 + 2 * S] & 0xffff; env.fruit[1] = r[REC_SNAKE0 + 2 * S] >> 16;
+  env.fruit[2] = r[REC_SNAKE0 + 2 * S + 1] & 0xffff; env.fruit[3] = r[REC_SNAKE0 + 2 * S + 1] >> 16;
+}
+
+template <int S>
+__device__ __forceinline__ void lane_store(const Params& p, long long e, const LaneEnv<S>& env) {
+  constexpr int RW = LaneRec<S>::RW;
+  u32 r[RW];
+#pragma unroll
+  for (int i = 0; i < RW; ++i) r[i] = 0;
+  r[REC_T] = env.t; r[REC_EP_LEN] = env.ep_len; r[REC_DRAW_CTR] = env.ctr; r[REC_EP_RET] = __float_as_uint(env.ep_ret);
+  r[REC_SPARE] = env.spare;
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    r[REC_SNAKE0 + 2 * s] = (u32)env.head[s] | ((u32)env.len[s] << 16);
+    r[REC_SNAKE0 + 2 * s + 1] = (u32)env.grow[s] | ((u32)env.vel[s] << 16);
+    p.chain[(e * S + s) * p.CW] = env.c0[s];
+  }
+  r[REC_SNAKE0 + 2 * S] = (u32)env.fruit[0] | ((u32)env.fruit[1] << 16);
+  r[REC_SNAKE0 + 2 * S + 1] = (u32)env.fruit[2] | ((u32)env.fruit[3] << 16);
+  uint4* g = reinterpret_cast<uint4*>(p.rec + e * RW);
+#pragma unroll
+  for (int i = 0; i < RW / 4; ++i) g[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+}
+
+// Paint (PAINT) or un-paint one env into its image slot, done by the LPE lanes that share the env;
+// lane `sub` owns bytes sub, sub+LPE, ... of every pixel, so writes to one byte are always issued by
+// the same lane in program order: fruits first, then snakes by index (get_ob_for_snake :35-58).
+// Out-of-board cells are skipped (the reference paints them under the border, :52-56).
+template <int S, int RULES, bool PAINT>
+__device__ __forceinline__ void lane_paint(const Params& p, const LaneEnv<S>& env, bool valid, long long e_owner, int owner,
+                                           int sub, int LPE, u8* img) {
+  const int C = p.C, V = p.V, F = p.F;
+  const bool ov = __shfl_sync(FULL, (int)valid, owner);
+  if (RULES == SNK_RULES_CLASSIC) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      const int fp = __shfl_sync(FULL, env.fruit[f], owner);
+      if (ov && f < F)
+        for (int b = sub; b < C; b += LPE) if (b - 3 * ((b * 11) >> 5) == 0) img[fp * C + b] = PAINT ? 255 : 0;
+    }
+  } else if (ov) {
+    const u32* g32 = reinterpret_cast<const u32*>(p.grid + e_owner * p.grid_stride);
+    for (int w = 0; w < (p.VV + 3) / 4; ++w) {
+      u32 word = g32[w];
+      for (int q = 0; word; ++q, word >>= 8) {
+        const int pid = 4 * w + q;
+        if ((word & 0xff) && pid < p.VV && !(__ldg(p.cellinfo + pid) >> 31))
+          for (int b = sub; b < C; b += LPE) if (b - 3 * ((b * 11) >> 5) == 0) img[pid * C + b] = PAINT ? 255 : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int h = __shfl_sync(FULL, env.head[s], owner);
+    const int L = __shfl_sync(FULL, env.len[s], owner);
+    const u32 c = __shfl_sync(FULL, env.c0[s], owner);
+    if (!ov) continue;
+    chain_walk(h, L, c, p.chain + (e_owner * S + s) * p.CW, V, [&](int i, int pid) {
+      for (int b = sub; b < C; b += LPE) {
+        const int k = (b * 11) >> 5, ch = b - 3 * k;  // view, channel of byte b (b < 32)
+        img[pid * C + b] = PAINT ? (u8)(snake_rgb(s == k, i == 0) >> (8 * ch)) : (u8)0;
+      }
+    });
+  }
+}

@@ -6,16 +6,17 @@
 #include "../../include/snk.h"
 
 struct Params;
+enum { KIND_LANE = 0, KIND_TILE = 1, KIND_DENSE = 2 };
 
 struct LaunchPlan {
-  bool use_tile;    // k_step_tile (warp per env, TMA image store) or k_step_dense (CTA per env)
+  int kind;         // KIND_LANE (lane per env, chain bodies), KIND_TILE (warp per env) or KIND_DENSE (CTA per env)
   int grid, block;
   size_t smem;
   int occupancy;    // resident CTAs per SM
   int max_grid;     // SMs * occupancy: persistent grid size
 };
 
-cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm);
+cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm, int S);
 cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, cudaStream_t stream);
 cudaError_t snk_launch_dump(const Params& p, uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);
 cudaError_t snk_launch_load(const Params& p, const uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);

@@ -286,7 +286,9 @@ class SnakeVecEnv(object):
     def launch_info(self):
         out = (C.c_int32 * 6)()
         _lib.check(self._L.snk_launch_info(self._h, out))
-        return dict(zip(("use_tile", "grid", "block", "smem", "occupancy", "envs_per_cta"), list(out)))
+        d = dict(zip(("kind", "grid", "block", "smem", "occupancy", "envs_per_cta"), list(out)))
+        d["kernel"] = ("k_step_lane", "k_step_tile", "k_step_dense")[d["kind"]]
+        return d
 
     def algorithmic_bytes_per_step(self, mean_sum_len):
         out = C.c_double(0)

@@ -93,7 +93,9 @@ CONFIGS = [
     ("adversarial", 2, 5, 2, 2, 129, 400),
     ("cut", 3, 10, 3, 3, 512, 400),          # configs[2]
     ("cut", 5, 8, 5, 5, 200, 400),
-    ("classic", 2, 30, 2, 2, 64, 200),       # largest board of the tile kernel class
+    ("classic", 2, 30, 2, 2, 64, 200),       # large board, still the lane kernel class
+    ("classic", 5, 12, 5, 5, 100, 200),      # S = 5: outside the lane kernel class -> tile kernel
+    ("classic", 2, 40, 2, 2, 40, 100),       # D = 40: outside the lane kernel class -> tile kernel
 ]
 
 
@@ -185,19 +187,28 @@ def test_known_answers(sb):
         env.close()
 
 
-def test_dense_kernel_matches_oracle(sb, monkeypatch):
-    """The CTA-per-env kernel (large boards) forced onto small configs, and on a 16-snake 64x64 field."""
-    monkeypatch.setenv("SNK_FORCE_KERNEL", "dense")
+@pytest.mark.parametrize("kernel", ["tile", "dense"])
+def test_general_kernels_match_oracle(sb, monkeypatch, kernel):
+    """The warp-per-env tile kernel and the CTA-per-env dense kernel (used for boards outside the
+    lane kernel's class) forced onto small configs."""
+    monkeypatch.setenv("SNK_FORCE_KERNEL", kernel)
     for rules, S, D, N, steps in (("classic", 2, 19, 100, 150), ("adversarial", 3, 10, 100, 200), ("cut", 3, 10, 100, 200)):
         kw = dict(size=D, n_snakes=S, rules=rules, seed=11)
         env = sb.SnakeVecEnv(N, **kw)
-        assert not env.launch_info()["use_tile"]
+        assert env.launch_info()["kernel"] == "k_step_" + kernel
         co = c_oracle.COracle(N, **kw)
         assert np.array_equal(env.reset().cpu().numpy(), co.reset())
         for t in range(steps):
             a = c_oracle.gen_actions(co.cfg, t, 5, env.action_space.n)
-            _compare_step(env, co, a, "dense %s step %d" % (rules, t), check_state=(t % 10 == 0))
+            _compare_step(env, co, a, "%s %s step %d" % (kernel, rules, t), check_state=(t % 10 == 0))
         env.close()
+    monkeypatch.delenv("SNK_FORCE_KERNEL")
+
+
+def test_tile_kernel_golden_replay(sb, monkeypatch):
+    """The tile kernel also replays the reference recording of the headline geometry."""
+    monkeypatch.setenv("SNK_FORCE_KERNEL", "tile")
+    test_golden_replay(sb, "classic_2x19")
     monkeypatch.delenv("SNK_FORCE_KERNEL")
 
 
