@@ -155,7 +155,7 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   LaunchPlan& plan = h->plan;
   const char* force = getenv("SNK_FORCE_KERNEL");  // "lane" | "tile" | "dense": testing aid
   int TE = 0;
-  if (S <= 4 && F <= 4 && D <= 32 && K <= 8) {
+  if (snk_lane_supported(S, K) && F <= 4 && D <= 32) {
     const int cand[3] = {32, 16, 8};
     for (int i = 0; i < 3 && !TE; ++i)
       if (cand[i] % p.G == 0 && (size_t)cand[i] * p.E <= 28 * 1024) TE = cand[i];
@@ -183,7 +183,7 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     p.n_groups = N;
     if (plan.smem > 200 * 1024) { snk_destroy(h); return fail(SNK_EINVAL, "board too large for shared memory"); }
   }
-  CUDA_TRY_H(snk_plan(cfg->rules, plan, h->n_sm, S));
+  CUDA_TRY_H(snk_plan(cfg->rules, plan, h->n_sm, S, K));
   {
     const long long work = plan.kind == KIND_LANE ? (p.n_groups + 1) / 2 : p.n_groups;  // lane: 2 warps per CTA
     plan.grid = (int)(work < plan.max_grid ? work : plan.max_grid);

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(BLOCK) k_step_tile(const Params p) {
 
 // k_step_lane: see snk_lane.cuh.  A warp is an independent worker: 32 envs of logic (one per lane),
 // then 32/TE rounds of paint -> TMA bulk store -> un-paint on its private image.  No __syncthreads.
-template <int S, int RULES>
+template <int S, int RULES, int K>
 __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   extern __shared__ __align__(128) u8 smem[];
   __shared__ double s_stats[SNK_NSTATS];
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
       const long long e0 = b * 32 + (long long)q * TE;
       if (e0 >= p.N) break;
       const int owner = q * TE + slot;
-      lane_paint<S, RULES, true>(p, env, valid, e0 + slot, owner, sub, LPE, img);
+      lane_paint<S, RULES, K, true>(p, env, valid, e0 + slot, owner, sub, LPE, img);
       fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
       __syncwarp();
       const long long left = p.N - e0;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
         for (int i = lane; i < bytes; i += 32) gdst[i] = tile[i];
       }
       __syncwarp();
-      lane_paint<S, RULES, false>(p, env, valid, e0 + slot, owner, sub, LPE, img);
+      lane_paint<S, RULES, K, false>(p, env, valid, e0 + slot, owner, sub, LPE, img);
       __syncwarp();
     }
   }
@@ -383,21 +383,23 @@ __global__ void k_gen_actions(int8_t* actions, long long N, int S, long long env
 }
 
 // ------------------------------------------------------------------ launchers
-template <int S, int RULES>
-static cudaError_t launch_lane(const Params& p, const LaunchPlan& plan, cudaStream_t stream) {
-  k_step_lane<S, RULES><<<plan.grid, plan.block, plan.smem, stream>>>(p);
-  return cudaGetLastError();
+// (S, K) pairs the lane kernel is compiled for: one view per snake, or the 3 views SnakeEnv emits
+#define LANE_COMBOS(X) X(1, 1) X(2, 2) X(3, 3) X(4, 4) X(1, 3) X(2, 3)
+
+bool snk_lane_supported(int S, int K) {
+#define X(s, k) if (S == s && K == k) return true;
+  LANE_COMBOS(X)
+#undef X
+  return false;
 }
 
 template <int RULES>
 static cudaError_t launch_rules(const Params& p, const LaunchPlan& plan, cudaStream_t stream) {
   if (plan.kind == KIND_LANE) {
-    switch (p.S) {
-      case 1: return launch_lane<1, RULES>(p, plan, stream);
-      case 2: return launch_lane<2, RULES>(p, plan, stream);
-      case 3: return launch_lane<3, RULES>(p, plan, stream);
-      default: return launch_lane<4, RULES>(p, plan, stream);
-    }
+#define X(s, k) if (p.S == s && p.K == k) { k_step_lane<s, RULES, k><<<plan.grid, plan.block, plan.smem, stream>>>(p); return cudaGetLastError(); }
+    LANE_COMBOS(X)
+#undef X
+    return cudaErrorInvalidConfiguration;
   }
   if (plan.kind == KIND_TILE) {
     if (plan.block <= 256) k_step_tile<RULES, 256><<<plan.grid, plan.block, plan.smem, stream>>>(p);
@@ -416,24 +418,21 @@ cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, 
   }
 }
 
-template <int S, int RULES>
+template <int S, int RULES, int K>
 static cudaError_t plan_lane(LaunchPlan& plan, int& occ) {
   cudaError_t err;
-  if ((err = cudaFuncSetAttribute(k_step_lane<S, RULES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_lane<S, RULES>, plan.block, plan.smem);
+  if ((err = cudaFuncSetAttribute(k_step_lane<S, RULES, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_lane<S, RULES, K>, plan.block, plan.smem);
 }
 
 template <int RULES>
-static cudaError_t plan_rules(LaunchPlan& plan, int n_sm, int S) {
-  cudaError_t err;
+static cudaError_t plan_rules(LaunchPlan& plan, int n_sm, int S, int K) {
+  cudaError_t err = cudaErrorInvalidConfiguration;
   int occ = 0;
   if (plan.kind == KIND_LANE) {
-    switch (S) {
-      case 1: err = plan_lane<1, RULES>(plan, occ); break;
-      case 2: err = plan_lane<2, RULES>(plan, occ); break;
-      case 3: err = plan_lane<3, RULES>(plan, occ); break;
-      default: err = plan_lane<4, RULES>(plan, occ); break;
-    }
+#define X(s, k) if (S == s && K == k) err = plan_lane<s, RULES, k>(plan, occ);
+    LANE_COMBOS(X)
+#undef X
     if (err) return err;
   } else if (plan.kind == KIND_TILE && plan.block <= 256) {
     if ((err = cudaFuncSetAttribute(k_step_tile<RULES, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
@@ -451,11 +450,11 @@ static cudaError_t plan_rules(LaunchPlan& plan, int n_sm, int S) {
   return cudaSuccess;
 }
 
-cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm, int S) {
+cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm, int S, int K) {
   switch (rules) {
-    case SNK_RULES_CLASSIC: return plan_rules<SNK_RULES_CLASSIC>(plan, n_sm, S);
-    case SNK_RULES_ADVERSARIAL: return plan_rules<SNK_RULES_ADVERSARIAL>(plan, n_sm, S);
-    default: return plan_rules<SNK_RULES_CUT>(plan, n_sm, S);
+    case SNK_RULES_CLASSIC: return plan_rules<SNK_RULES_CLASSIC>(plan, n_sm, S, K);
+    case SNK_RULES_ADVERSARIAL: return plan_rules<SNK_RULES_ADVERSARIAL>(plan, n_sm, S, K);
+    default: return plan_rules<SNK_RULES_CUT>(plan, n_sm, S, K);
   }
 }
 

@@ -331,44 +331,79 @@ __device__ __forceinline__ void lane_store(const Params& p, long long e, const L
   for (int i = 0; i < RW / 4; ++i) g[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
 }
 
-// Paint (PAINT) or un-paint one env into its image slot, done by the LPE lanes that share the env;
-// lane `sub` owns bytes sub, sub+LPE, ... of every pixel, so writes to one byte are always issued by
-// the same lane in program order: fruits first, then snakes by index (get_ob_for_snake :35-58).
+// Position of segment i without walking: the 2-bit codes before it are counted per direction with
+// popcounts, pid_i = head - V*(#(+V) - #(-V)) - (#(+1) - #(-1)).
+__device__ __forceinline__ int chain_pos(int head, u32 c0, const u32* __restrict__ ch, int V, int i) {
+  int nV = 0, n1 = 0;
+  u32 w = c0;
+  int k = 0;
+  for (; i - 16 * k > 16; ++k) {  // whole words before the one holding code i-1 (bodies longer than 17)
+    const u32 lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+    nV += 16 - __popc(lo | hi) - __popc(hi & ~lo);
+    n1 += __popc(lo & ~hi) - __popc(lo & hi);
+    w = ch[k + 1];
+  }
+  const int r = i - 16 * k;  // 0..16 codes of word k
+  const u32 m = r >= 16 ? 0x55555555u : ((1u << (2 * r)) - 1u) & 0x55555555u;
+  const u32 lo = w & m, hi = (w >> 1) & m;
+  nV += r - __popc(lo | hi) - __popc(hi & ~lo);
+  n1 += __popc(lo & ~hi) - __popc(lo & hi);
+  return head - V * nV - n1;
+}
+
+// all C = 3K bytes of one pixel: snake s seen by every view k (self colours iff s == k)
+template <int S, int K, bool PAINT>
+__device__ __forceinline__ void put_pixel(u8* px, int s, bool is_head) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const u32 rgb = PAINT ? snake_rgb(s == k, is_head) : 0u;
+    px[3 * k] = (u8)rgb; px[3 * k + 1] = (u8)(rgb >> 8); px[3 * k + 2] = (u8)(rgb >> 16);
+  }
+}
+
+// Paint (PAINT) or un-paint the TE envs of one image.  The LPE lanes that share an env split its
+// fruits and, per snake, its segments (segment i goes to lane i % LPE; chain_pos makes that O(1)).
+// The reference's paint order (fruits, then snakes by index, get_ob_for_snake :35-58) is kept by a
+// __syncwarp between the groups; within a group two items never overlap with different colours.
 // Out-of-board cells are skipped (the reference paints them under the border, :52-56).
-template <int S, int RULES, bool PAINT>
+template <int S, int RULES, int K, bool PAINT>
 __device__ __forceinline__ void lane_paint(const Params& p, const LaneEnv<S>& env, bool valid, long long e_owner, int owner,
                                            int sub, int LPE, u8* img) {
-  const int C = p.C, V = p.V, F = p.F;
+  constexpr int C = 3 * K;
+  const int V = p.V, F = p.F;
   const bool ov = __shfl_sync(FULL, (int)valid, owner);
   if (RULES == SNK_RULES_CLASSIC) {
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
       const int fp = __shfl_sync(FULL, env.fruit[f], owner);
-      if (ov && f < F)
-        for (int b = sub; b < C; b += LPE) if (b - 3 * ((b * 11) >> 5) == 0) img[fp * C + b] = PAINT ? 255 : 0;
+      if (ov && f < F && (f & (LPE - 1)) == sub) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) img[fp * C + 3 * k] = PAINT ? 255 : 0;
+      }
     }
   } else if (ov) {
     const u32* g32 = reinterpret_cast<const u32*>(p.grid + e_owner * p.grid_stride);
-    for (int w = 0; w < (p.VV + 3) / 4; ++w) {
+    for (int w = sub; w < (p.VV + 3) / 4; w += LPE) {
       u32 word = g32[w];
       for (int q = 0; word; ++q, word >>= 8) {
         const int pid = 4 * w + q;
-        if ((word & 0xff) && pid < p.VV && !(__ldg(p.cellinfo + pid) >> 31))
-          for (int b = sub; b < C; b += LPE) if (b - 3 * ((b * 11) >> 5) == 0) img[pid * C + b] = PAINT ? 255 : 0;
+        if ((word & 0xff) && pid < p.VV && !(__ldg(p.cellinfo + pid) >> 31)) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) img[pid * C + 3 * k] = PAINT ? 255 : 0;
+        }
       }
     }
   }
+  if (PAINT) __syncwarp();
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     const int h = __shfl_sync(FULL, env.head[s], owner);
     const int L = __shfl_sync(FULL, env.len[s], owner);
     const u32 c = __shfl_sync(FULL, env.c0[s], owner);
-    if (!ov) continue;
-    chain_walk(h, L, c, p.chain + (e_owner * S + s) * p.CW, V, [&](int i, int pid) {
-      for (int b = sub; b < C; b += LPE) {
-        const int k = (b * 11) >> 5, ch = b - 3 * k;  // view, channel of byte b (b < 32)
-        img[pid * C + b] = PAINT ? (u8)(snake_rgb(s == k, i == 0) >> (8 * ch)) : (u8)0;
-      }
-    });
+    if (ov) {
+      const u32* ch = p.chain + (e_owner * S + s) * p.CW;
+      for (int i = sub; i < L; i += LPE) put_pixel<S, K, PAINT>(img + chain_pos(h, c, ch, V, i) * C, s, i == 0);
+    }
+    if (PAINT) __syncwarp();
   }
 }

@@ -16,7 +16,8 @@ struct LaunchPlan {
   int max_grid;     // SMs * occupancy: persistent grid size
 };
 
-cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm, int S);
+cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm, int S, int K);
+bool snk_lane_supported(int S, int K);
 cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, cudaStream_t stream);
 cudaError_t snk_launch_dump(const Params& p, uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);
 cudaError_t snk_launch_load(const Params& p, const uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);
