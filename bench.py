@@ -329,7 +329,7 @@ def run_ours(args):
                                  "note": "obs stays in HBM for an on-device learner; actions H2D, reward+done D2H every step"},
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_step_tile<classic,256>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": env.launch_info()["kernel"],
                          "algorithmic_bytes_per_env_step": alg_bytes, "env_steps_per_launch": N,
                          "launch_us": launch_s * 1e6},
             "episode_stats": stats,

@@ -168,12 +168,27 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   if (force && !strcmp(force, "tile") && smem_tile <= 200 * 1024) plan.kind = KIND_TILE;
   if (force && !strcmp(force, "lane") && !TE) { snk_destroy(h); return fail(SNK_EINVAL, "lane kernel does not support this configuration"); }
   p.family = plan.kind == KIND_LANE;
+  { const char* sm = getenv("SNK_STORE"); p.store_mode = (sm && !strcmp(sm, "stg")) ? 1 : 0; }
+  { const char* dbg = getenv("SNK_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+  int logic_warps = 3;
+  // lane path variants (SNK_LANE=fused|ws|split, testing aid): every warp steps 32 envs then streams
+  // their images (default: fastest measured), warp-specialised single kernel, or two kernels
+  {
+    const char* lv = getenv("SNK_LANE");
+    plan.ws = plan.kind == KIND_LANE && lv && !strcmp(lv, "ws");
+    plan.split = plan.kind == KIND_LANE && lv && !strcmp(lv, "split");
+    const char* lw = getenv("SNK_LOGIC_WARPS");
+    p.PW = 2;
+    logic_warps = lw ? atoi(lw) : 3;
+    if (logic_warps < 1 || logic_warps > 3) logic_warps = 3;
+  }
   p.CW = (p.cap - 1 + 15) / 16;
   if (plan.kind == KIND_LANE) {
     p.RW = (REC_SNAKE0 + 2 * S + 2 + 3) & ~3;
     p.TE = TE; p.W = 32;
     p.tile_stride = (int)(((size_t)TE * p.E + 127) & ~(size_t)127);
-    plan.block = 64; plan.smem = (size_t)2 * p.tile_stride;
+    plan.block = plan.ws ? 32 * (p.PW + logic_warps) : 64;
+    plan.smem = (size_t)2 * p.tile_stride;
     p.n_groups = (N + 31) / 32;
   } else if (plan.kind == KIND_TILE) {
     p.W = W; plan.block = 32 * W; plan.smem = smem_tile;
@@ -185,7 +200,9 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   }
   CUDA_TRY_H(snk_plan(cfg->rules, plan, h->n_sm, S, K));
   {
-    const long long work = plan.kind == KIND_LANE ? (p.n_groups + 1) / 2 : p.n_groups;  // lane: 2 warps per CTA
+    long long work = plan.kind == KIND_LANE ? (p.n_groups + 1) / 2 : p.n_groups;  // lane: 2 warps per CTA
+    if (plan.split) work = ((N + p.TE - 1) / p.TE + 1) / 2;                       // paint kernel: one image per warp
+    if (plan.ws) { const int LW = plan.block / 32 - p.PW; work = (p.n_groups + LW - 1) / LW; }
     plan.grid = (int)(work < plan.max_grid ? work : plan.max_grid);
     if (plan.grid < 1) plan.grid = 1;
   }
@@ -263,7 +280,7 @@ static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_
   p.tape_vals = h->d_tape_vals; p.tape_bounds = h->d_tape_bounds; p.tape_off = h->d_tape_off;
   if (p.rng_mode == SNK_RNG_TAPE && !p.tape_vals) return fail(SNK_EINVAL, "rng_mode is TAPE but no tape was set");
   CUDA_TRY(snk_launch_step(p, h->cfg.rules, h->plan, stream));
-  h->launches++;
+  h->launches += (h->plan.split && mode != MODE_OBSERVE) ? 2 : 1;
   return SNK_OK;
 }
 

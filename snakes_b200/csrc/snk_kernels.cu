@@ -152,6 +152,204 @@ __global__ void __launch_bounds__(BLOCK) k_step_tile(const Params p) {
 }
 
 
+// Stream one painted image (TE envs, 16-byte aligned in HBM) out of shared memory: one TMA bulk
+// copy issued by lane 0 (which then waits until the engine has READ the image, so it may be
+// modified), or LDS.128 + STG.128 by all lanes; the last, partial image uses plain byte stores.
+__device__ __forceinline__ void store_image(const Params& p, const u8* tile, int tile_bytes, long long e0, int lane) {
+  const long long left = p.N - e0;
+  u8* gdst = p.obs + e0 * (long long)p.E;
+  if (left >= p.TE && p.store_mode == 0) {
+    if (lane == 0) {
+      for (int off = 0; off < tile_bytes; off += 16384)
+        bulk_store_s2g(gdst + off, tile + off, (u32)min(16384, tile_bytes - off));
+      bulk_commit();
+      bulk_wait_read();
+    }
+  } else if (left >= p.TE) {
+    const uint4* src = reinterpret_cast<const uint4*>(tile);
+    uint4* dst = reinterpret_cast<uint4*>(gdst);
+    const int n16 = tile_bytes / 16;
+    int i = lane;
+    for (; i + 96 < n16; i += 128) {  // 4 independent 16-byte loads in flight per lane
+      const uint4 a = src[i], b = src[i + 32], c = src[i + 64], d = src[i + 96];
+      __stcs(dst + i, a); __stcs(dst + i + 32, b); __stcs(dst + i + 64, c); __stcs(dst + i + 96, d);
+    }
+    for (; i < n16; i += 32) __stcs(dst + i, src[i]);
+  } else {
+    const int bytes = (int)left * p.E;
+    for (int i = lane; i < bytes; i += 32) gdst[i] = tile[i];
+  }
+}
+
+__device__ __forceinline__ void init_border_image(const Params& p, u8* tile, int lane) {
+  const uint4* src = reinterpret_cast<const uint4*>(p.tmpl);
+  const int n16 = p.G * p.E / 16;
+  for (int c = 0; c < p.TE / p.G; ++c) {
+    uint4* dst = reinterpret_cast<uint4*>(tile + c * p.G * p.E);
+    for (int i = lane; i < n16; i += 32) dst[i] = src[i];
+  }
+}
+
+__device__ __forceinline__ void reduce_lane_stats(const Params& p, LaneStats st, u32 errs, double* s_stats, int lane) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    st.steps += __shfl_xor_sync(FULL, st.steps, o); st.episodes += __shfl_xor_sync(FULL, st.episodes, o);
+    st.ret_sum += __shfl_xor_sync(FULL, st.ret_sum, o); st.len_sum += __shfl_xor_sync(FULL, st.len_sum, o);
+    st.fruits += __shfl_xor_sync(FULL, st.fruits, o); st.deaths += __shfl_xor_sync(FULL, st.deaths, o);
+    st.cells += __shfl_xor_sync(FULL, st.cells, o); st.draws += __shfl_xor_sync(FULL, st.draws, o);
+    errs |= __shfl_xor_sync(FULL, errs, o);
+  }
+  WarpStats ws = {st.steps, st.episodes, st.ret_sum, st.len_sum, st.fruits, st.deaths, st.cells, st.draws};
+  flush_stats(p, ws, errs, s_stats, lane);
+}
+
+// ---- split form of the lane path: game logic at full occupancy, then the observation writer.
+// k_lane_logic: one THREAD per env, no shared-memory image, so many warps per SM hide the HBM
+// latency of the record / chain / action loads.
+template <int S, int RULES>
+__global__ void __launch_bounds__(128) k_lane_logic(const Params p) {
+  __shared__ double s_stats[SNK_NSTATS];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  __syncthreads();
+  LaneStats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  u32 errs = 0;
+  const long long e = (long long)blockIdx.x * blockDim.x + tid;
+  if (e < p.N) {
+    LaneEnv<S> env;
+    LaneRng rng;
+    rng.have = false; rng.blk = 0;
+    u8* grid = p.grid ? p.grid + e * p.grid_stride : nullptr;
+    lane_load<S>(p, e, env);
+    if (p.mode == MODE_STEP) {
+      lane_step<S, RULES>(p, e, env, rng, grid, errs, st);
+    } else if (!p.mask || p.mask[e]) {
+      lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);
+    }
+    lane_store<S>(p, e, env);
+  }
+  reduce_lane_stats(p, st, errs, s_stats, lane);
+  __syncthreads();
+  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+}
+
+// k_lane_paint: the observation writer.  Each warp owns one shared-memory image of TE envs holding
+// the border and loops over images: the records of the NEXT image are prefetched, the current one is
+// painted (LPE lanes per env), handed to the TMA engine, and un-painted once the engine has read it.
+// The image buffers are the scarce resource (10 per SM at 2x19x19); this kernel keeps them busy.
+template <int S, int RULES, int K>
+__global__ void __launch_bounds__(64) k_lane_paint(const Params p) {
+  extern __shared__ __align__(128) u8 smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int TE = p.TE, LPE = 32 / TE, E = p.E;
+  const int tile_bytes = TE * E;
+  u8* tile = smem + warp * p.tile_stride;
+  init_border_image(p, tile, lane);
+  __syncwarp();
+  const int slot = lane / LPE, sub = lane - slot * LPE;
+  u8* img = tile + slot * E;
+  const long long n_items = (p.N + TE - 1) / TE;
+  const long long stride = (long long)gridDim.x * wpc;
+  long long item = (long long)blockIdx.x * wpc + warp;
+  PaintEnv<S> cur = paint_env_from_memory<S>(p, item < n_items ? item * TE + slot : p.N);
+  while (item < n_items) {
+    const long long next = item + stride;
+    const PaintEnv<S> nxt = paint_env_from_memory<S>(p, next < n_items ? next * TE + slot : p.N);
+    const long long e0 = item * TE;
+    if (!(p.debug & 1)) lane_paint<S, RULES, K, true>(p, cur, e0 + slot, sub, LPE, img);
+    fence_async_smem();
+    __syncwarp();
+    if (!(p.debug & 2)) store_image(p, tile, tile_bytes, e0, lane);
+    __syncwarp();
+    if (!(p.debug & 1)) lane_paint<S, RULES, K, false>(p, cur, e0 + slot, sub, LPE, img);
+    __syncwarp();
+    cur = nxt;
+    item = next;
+  }
+  if (lane == 0) bulk_wait_all();
+}
+
+
+// k_step_lane_ws: ONE fused launch, warp-specialised.  Each CTA has PW "paint" warps, each owning a
+// shared-memory image (the scarce resource: 10 per SM at 2x19x19), and LW "logic" warps that own
+// nothing but registers.  Logic warps step 32 envs per iteration (one per lane) and publish a
+// per-warp round counter in shared memory; paint warps wait for the counter of the batch they
+// need, read its records back from L2, paint -> stream out -> un-paint.  Logic never waits, so the
+// record / action latency of later batches hides under the HBM write stream of earlier ones.
+template <int S, int RULES, int K>
+__global__ void __launch_bounds__(160, 5) k_step_lane_ws(const Params p) {
+  extern __shared__ __align__(128) u8 smem[];
+  __shared__ double s_stats[SNK_NSTATS];
+  __shared__ int s_ready[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int PW = p.PW, LW = (blockDim.x >> 5) - PW;
+  const int TE = p.TE, LPE = 32 / TE, E = p.E, IPB = 32 / TE;  // images per 32-env batch
+  if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  if (tid < 8) s_ready[tid] = 0;
+  __syncthreads();
+  const long long n_batches = (p.N + 31) / 32;
+  LaneStats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  u32 errs = 0;
+  if (warp < PW) {
+    // ------------------------------------------------------------ paint warp
+    const int tile_bytes = TE * E;
+    u8* tile = smem + warp * p.tile_stride;
+    init_border_image(p, tile, lane);
+    __syncwarp();
+    const int slot = lane / LPE, sub = lane - slot * LPE;
+    u8* img = tile + slot * E;
+    volatile int* ready = s_ready;
+    for (int r = 0;; ++r) {
+      const long long base_b = ((long long)r * gridDim.x + blockIdx.x) * LW;
+      if (base_b >= n_batches) break;
+      for (int j = warp; j < LW * IPB; j += PW) {
+        const int l = j / IPB, q = j - l * IPB;
+        const long long e0 = (base_b + l) * 32 + (long long)q * TE;
+        if (e0 >= p.N) continue;
+        while (ready[l] <= r) __nanosleep(64);
+        __threadfence_block();
+        const PaintEnv<S> pe = paint_env_from_memory<S>(p, e0 + slot);
+        lane_paint<S, RULES, K, true>(p, pe, e0 + slot, sub, LPE, img);
+        fence_async_smem();
+        __syncwarp();
+        store_image(p, tile, tile_bytes, e0, lane);
+        __syncwarp();
+        lane_paint<S, RULES, K, false>(p, pe, e0 + slot, sub, LPE, img);
+        __syncwarp();
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+  } else {
+    // ------------------------------------------------------------ logic warp
+    const int lw = warp - PW;
+    for (int r = 0;; ++r) {
+      const long long base_b = ((long long)r * gridDim.x + blockIdx.x) * LW;
+      if (base_b >= n_batches) break;
+      const long long e = (base_b + lw) * 32 + lane;
+      if (e < p.N && p.mode != MODE_OBSERVE) {
+        LaneEnv<S> env;
+        LaneRng rng;
+        rng.have = false; rng.blk = 0;
+        u8* grid = p.grid ? p.grid + e * p.grid_stride : nullptr;
+        lane_load<S>(p, e, env);
+        if (p.mode == MODE_STEP) {
+          lane_step<S, RULES>(p, e, env, rng, grid, errs, st);
+        } else if (!p.mask || p.mask[e]) {
+          lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);
+        }
+        lane_store<S>(p, e, env);
+      }
+      __threadfence_block();  // records / chain words / fruit grid before the round counter
+      __syncwarp();
+      if (lane == 0) *(volatile int*)&s_ready[lw] = r + 1;
+    }
+  }
+  reduce_lane_stats(p, st, errs, s_stats, lane);
+  __syncthreads();
+  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+}
+
+
 // k_step_lane: see snk_lane.cuh.  A warp is an independent worker: 32 envs of logic (one per lane),
 // then 32/TE rounds of paint -> TMA bulk store -> un-paint on its private image.  No __syncthreads.
 template <int S, int RULES, int K>
@@ -162,14 +360,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   const int TE = p.TE, LPE = 32 / TE, E = p.E;
   const int tile_bytes = TE * E;
   u8* tile = smem + warp * p.tile_stride;
-  {  // border-only image of TE envs
-    const uint4* src = reinterpret_cast<const uint4*>(p.tmpl);
-    const int n16 = p.G * E / 16;
-    for (int c = 0; c < TE / p.G; ++c) {
-      uint4* dst = reinterpret_cast<uint4*>(tile + c * p.G * E);
-      for (int i = lane; i < n16; i += 32) dst[i] = src[i];
-    }
-  }
+  init_border_image(p, tile, lane);
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
   __syncthreads();
   LaneStats st = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -200,41 +391,18 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
     for (int q = 0; q < LPE; ++q) {
       const long long e0 = b * 32 + (long long)q * TE;
       if (e0 >= p.N) break;
-      const int owner = q * TE + slot;
-      lane_paint<S, RULES, K, true>(p, env, valid, e0 + slot, owner, sub, LPE, img);
+      const PaintEnv<S> pe = paint_env_from_lane<S>(env, valid, q * TE + slot);
+      lane_paint<S, RULES, K, true>(p, pe, e0 + slot, sub, LPE, img);
       fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
       __syncwarp();
-      const long long left = p.N - e0;
-      u8* gdst = p.obs + e0 * (long long)E;
-      if (left >= TE) {
-        if (lane == 0) {
-          for (int off = 0; off < tile_bytes; off += 16384)
-            bulk_store_s2g(gdst + off, tile + off, (u32)min(16384, tile_bytes - off));
-          bulk_commit();
-          bulk_wait_read();  // the engine has read the image: it may be modified again
-        }
-      } else {  // last, partial image: plain stores for the valid envs only
-        const int bytes = (int)left * E;
-        for (int i = lane; i < bytes; i += 32) gdst[i] = tile[i];
-      }
+      store_image(p, tile, tile_bytes, e0, lane);
       __syncwarp();
-      lane_paint<S, RULES, K, false>(p, env, valid, e0 + slot, owner, sub, LPE, img);
+      lane_paint<S, RULES, K, false>(p, pe, e0 + slot, sub, LPE, img);
       __syncwarp();
     }
   }
   if (lane == 0) bulk_wait_all();
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    st.steps += __shfl_xor_sync(FULL, st.steps, o); st.episodes += __shfl_xor_sync(FULL, st.episodes, o);
-    st.ret_sum += __shfl_xor_sync(FULL, st.ret_sum, o); st.len_sum += __shfl_xor_sync(FULL, st.len_sum, o);
-    st.fruits += __shfl_xor_sync(FULL, st.fruits, o); st.deaths += __shfl_xor_sync(FULL, st.deaths, o);
-    st.cells += __shfl_xor_sync(FULL, st.cells, o); st.draws += __shfl_xor_sync(FULL, st.draws, o);
-    errs |= __shfl_xor_sync(FULL, errs, o);
-  }
-  {
-    WarpStats ws = {st.steps, st.episodes, st.ret_sum, st.len_sum, st.fruits, st.deaths, st.cells, st.draws};
-    flush_stats(p, ws, errs, s_stats, lane);
-  }
+  reduce_lane_stats(p, st, errs, s_stats, lane);
   __syncthreads();
   if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
@@ -310,8 +478,9 @@ __global__ void k_dump(const Params p, u8* blob, snk_state_layout lay) {
   u16* dst = reinterpret_cast<u16*>(blob + lay.off_body) + i * cap;
   if (p.family == 1) {  // chain code: hs is the head id
     const u32* ch = p.chain + i * p.CW;
+    const u32 c0 = r[s < 3 ? 5 + s : p.RW - 2];  // LaneRec::c0_word
     for (int k = 0; k < cap; ++k) dst[k] = 0;
-    chain_walk(hs, len, ch[0], ch, p.V, [&](int k, int pid) { dst[k] = (u16)pid; });
+    chain_walk(hs, len, c0, ch, p.V, [&](int k, int pid) { dst[k] = (u16)pid; });
   } else {
     const u16* ring = p.body + i * cap;
     for (int k = 0; k < cap; ++k) dst[k] = k < len ? (u16)ring_at(ring, hs, k, cap) : (u16)0;
@@ -353,6 +522,7 @@ __global__ void k_load(const Params p, const u8* blob, snk_state_layout lay) {
       if (d == 4u) { atomicOr(p.err, SNK_DEVERR_BAD_STATE); break; }
       ch[k >> 4] |= d << (2 * (k & 15));
     }
+    r[s < 3 ? 5 + s : p.RW - 2] = ch[0];  // LaneRec::c0_word
   } else {
     r[REC_SNAKE0 + 2 * s] = 0u | (len << 16);
     u16* ring = p.body + i * cap;
@@ -364,7 +534,7 @@ __global__ void k_load(const Params p, const u8* blob, snk_state_layout lay) {
     r[REC_DRAW_CTR] = reinterpret_cast<const u32*>(blob + lay.off_draw_ctr)[e];
     r[REC_EP_RET] = reinterpret_cast<const u32*>(blob + lay.off_ep_ret)[e];
     r[REC_EP_LEN] = (u32) reinterpret_cast<const int32_t*>(blob + lay.off_ep_len)[e];
-    r[5] = r[6] = r[7] = 0;
+    if (p.family == 0) r[5] = r[6] = r[7] = 0;
     if (lay.fruit_is_grid) {
       for (int k = 0; k < p.VV; ++k) p.grid[e * p.grid_stride + k] = (blob + lay.off_fruit)[e * p.VV + k];
     } else {
@@ -396,7 +566,18 @@ bool snk_lane_supported(int S, int K) {
 template <int RULES>
 static cudaError_t launch_rules(const Params& p, const LaunchPlan& plan, cudaStream_t stream) {
   if (plan.kind == KIND_LANE) {
-#define X(s, k) if (p.S == s && p.K == k) { k_step_lane<s, RULES, k><<<plan.grid, plan.block, plan.smem, stream>>>(p); return cudaGetLastError(); }
+#define X(s, k)                                                                                              \
+  if (p.S == s && p.K == k) {                                                                                \
+    if (plan.ws) {                                                                                           \
+      k_step_lane_ws<s, RULES, k><<<plan.grid, plan.block, plan.smem, stream>>>(p);                          \
+    } else if (!plan.split) {                                                                                \
+      k_step_lane<s, RULES, k><<<plan.grid, plan.block, plan.smem, stream>>>(p);                             \
+    } else {                                                                                                 \
+      if (p.mode != MODE_OBSERVE) k_lane_logic<s, RULES><<<(unsigned)((p.N + 127) / 128), 128, 0, stream>>>(p); \
+      k_lane_paint<s, RULES, k><<<plan.grid, plan.block, plan.smem, stream>>>(p);                            \
+    }                                                                                                        \
+    return cudaGetLastError();                                                                               \
+  }
     LANE_COMBOS(X)
 #undef X
     return cudaErrorInvalidConfiguration;
@@ -421,6 +602,14 @@ cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, 
 template <int S, int RULES, int K>
 static cudaError_t plan_lane(LaunchPlan& plan, int& occ) {
   cudaError_t err;
+  if (plan.ws) {
+    if ((err = cudaFuncSetAttribute(k_step_lane_ws<S, RULES, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_lane_ws<S, RULES, K>, plan.block, plan.smem);
+  }
+  if (plan.split) {
+    if ((err = cudaFuncSetAttribute(k_lane_paint<S, RULES, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lane_paint<S, RULES, K>, plan.block, plan.smem);
+  }
   if ((err = cudaFuncSetAttribute(k_step_lane<S, RULES, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_lane<S, RULES, K>, plan.block, plan.smem);
 }

@@ -23,6 +23,9 @@
 template <int S>
 struct LaneRec {  // record words of the lane family: header 8, snakes 2S, room for 4 fruits
   static constexpr int RW = (REC_SNAKE0 + 2 * S + 2 + 3) & ~3;
+  // the first chain word (16 directions) of every snake lives INSIDE the record, so a typical step
+  // touches one contiguous 64-byte record per env and nothing else: words 5..7, snake 3 -> RW-2
+  __host__ __device__ static constexpr int c0_word(int s) { return s < 3 ? 5 + s : RW - 2; }
 };
 
 template <int S>
@@ -304,7 +307,7 @@ __device__ __forceinline__ void lane_load(const Params& p, long long e, LaneEnv<
   for (int s = 0; s < S; ++s) {
     env.head[s] = r[REC_SNAKE0 + 2 * s] & 0xffff; env.len[s] = r[REC_SNAKE0 + 2 * s] >> 16;
     env.grow[s] = r[REC_SNAKE0 + 2 * s + 1] & 0xffff; env.vel[s] = r[REC_SNAKE0 + 2 * s + 1] >> 16;
-    env.c0[s] = p.chain[(e * S + s) * p.CW];
+    env.c0[s] = r[LaneRec<S>::c0_word(s)];
   }
   env.fruit[0] = r[REC_SNAKE0 + 2 * S] & 0xffff; env.fruit[1] = r[REC_SNAKE0 + 2 * S] >> 16;
   env.fruit[2] = r[REC_SNAKE0 + 2 * S + 1] & 0xffff; env.fruit[3] = r[REC_SNAKE0 + 2 * S + 1] >> 16;
@@ -322,7 +325,7 @@ __device__ __forceinline__ void lane_store(const Params& p, long long e, const L
   for (int s = 0; s < S; ++s) {
     r[REC_SNAKE0 + 2 * s] = (u32)env.head[s] | ((u32)env.len[s] << 16);
     r[REC_SNAKE0 + 2 * s + 1] = (u32)env.grow[s] | ((u32)env.vel[s] << 16);
-    p.chain[(e * S + s) * p.CW] = env.c0[s];
+    r[LaneRec<S>::c0_word(s)] = env.c0[s];
   }
   r[REC_SNAKE0 + 2 * S] = (u32)env.fruit[0] | ((u32)env.fruit[1] << 16);
   r[REC_SNAKE0 + 2 * S + 1] = (u32)env.fruit[2] | ((u32)env.fruit[3] << 16);
@@ -361,27 +364,72 @@ __device__ __forceinline__ void put_pixel(u8* px, int s, bool is_head) {
   }
 }
 
+// What painting needs of one env: heads, lengths, first chain words, classic fruit ids.
+template <int S>
+struct PaintEnv {
+  int head[S], len[S];
+  u32 c0[S];
+  int fruit[4];
+  bool valid;
+};
+
+// fused kernel: the painting lane fetches the env of lane `owner` through shuffles
+template <int S>
+__device__ __forceinline__ PaintEnv<S> paint_env_from_lane(const LaneEnv<S>& env, bool valid, int owner) {
+  PaintEnv<S> pe;
+  pe.valid = __shfl_sync(FULL, (int)valid, owner);
+#pragma unroll
+  for (int f = 0; f < 4; ++f) pe.fruit[f] = __shfl_sync(FULL, env.fruit[f], owner);
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    pe.head[s] = __shfl_sync(FULL, env.head[s], owner);
+    pe.len[s] = __shfl_sync(FULL, env.len[s], owner);
+    pe.c0[s] = __shfl_sync(FULL, env.c0[s], owner);
+  }
+  return pe;
+}
+
+// split kernels: the painting lane reads the env's record from HBM / L2
+template <int S>
+__device__ __forceinline__ PaintEnv<S> paint_env_from_memory(const Params& p, long long e) {
+  constexpr int RW = LaneRec<S>::RW;
+  PaintEnv<S> pe;
+  pe.valid = e < p.N;
+#pragma unroll
+  for (int s = 0; s < S; ++s) { pe.head[s] = 0; pe.len[s] = 0; pe.c0[s] = 0; }
+  pe.fruit[0] = pe.fruit[1] = pe.fruit[2] = pe.fruit[3] = 0;
+  if (pe.valid) {
+    const u32* r = p.rec + e * RW;  // __ldcg: read at L2, the line may have just been written by another warp
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const u32 a = __ldcg(r + REC_SNAKE0 + 2 * s);
+      pe.head[s] = a & 0xffff; pe.len[s] = a >> 16;
+      pe.c0[s] = __ldcg(r + LaneRec<S>::c0_word(s));
+    }
+    const u32 f0 = __ldcg(r + REC_SNAKE0 + 2 * S), f1 = __ldcg(r + REC_SNAKE0 + 2 * S + 1);
+    pe.fruit[0] = f0 & 0xffff; pe.fruit[1] = f0 >> 16; pe.fruit[2] = f1 & 0xffff; pe.fruit[3] = f1 >> 16;
+  }
+  return pe;
+}
+
 // Paint (PAINT) or un-paint the TE envs of one image.  The LPE lanes that share an env split its
 // fruits and, per snake, its segments (segment i goes to lane i % LPE; chain_pos makes that O(1)).
 // The reference's paint order (fruits, then snakes by index, get_ob_for_snake :35-58) is kept by a
 // __syncwarp between the groups; within a group two items never overlap with different colours.
 // Out-of-board cells are skipped (the reference paints them under the border, :52-56).
 template <int S, int RULES, int K, bool PAINT>
-__device__ __forceinline__ void lane_paint(const Params& p, const LaneEnv<S>& env, bool valid, long long e_owner, int owner,
-                                           int sub, int LPE, u8* img) {
+__device__ __forceinline__ void lane_paint(const Params& p, const PaintEnv<S>& pe, long long e_owner, int sub, int LPE, u8* img) {
   constexpr int C = 3 * K;
   const int V = p.V, F = p.F;
-  const bool ov = __shfl_sync(FULL, (int)valid, owner);
   if (RULES == SNK_RULES_CLASSIC) {
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
-      const int fp = __shfl_sync(FULL, env.fruit[f], owner);
-      if (ov && f < F && (f & (LPE - 1)) == sub) {
+      if (pe.valid && f < F && (f & (LPE - 1)) == sub) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) img[fp * C + 3 * k] = PAINT ? 255 : 0;
+        for (int k = 0; k < K; ++k) img[pe.fruit[f] * C + 3 * k] = PAINT ? 255 : 0;
       }
     }
-  } else if (ov) {
+  } else if (pe.valid) {
     const u32* g32 = reinterpret_cast<const u32*>(p.grid + e_owner * p.grid_stride);
     for (int w = sub; w < (p.VV + 3) / 4; w += LPE) {
       u32 word = g32[w];
@@ -397,12 +445,9 @@ __device__ __forceinline__ void lane_paint(const Params& p, const LaneEnv<S>& en
   if (PAINT) __syncwarp();
 #pragma unroll
   for (int s = 0; s < S; ++s) {
-    const int h = __shfl_sync(FULL, env.head[s], owner);
-    const int L = __shfl_sync(FULL, env.len[s], owner);
-    const u32 c = __shfl_sync(FULL, env.c0[s], owner);
-    if (ov) {
+    if (pe.valid) {
       const u32* ch = p.chain + (e_owner * S + s) * p.CW;
-      for (int i = sub; i < L; i += LPE) put_pixel<S, K, PAINT>(img + chain_pos(h, c, ch, V, i) * C, s, i == 0);
+      for (int i = sub; i < pe.len[s]; i += LPE) put_pixel<S, K, PAINT>(img + chain_pos(pe.head[s], pe.c0[s], ch, V, i) * C, s, i == 0);
     }
     if (PAINT) __syncwarp();
   }

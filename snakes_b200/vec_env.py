@@ -288,6 +288,7 @@ class SnakeVecEnv(object):
         _lib.check(self._L.snk_launch_info(self._h, out))
         d = dict(zip(("kind", "grid", "block", "smem", "occupancy", "envs_per_cta"), list(out)))
         d["kernel"] = ("k_step_lane", "k_step_tile", "k_step_dense")[d["kind"]]
+        d["envs_per_cta"] = d["block"] if d["kind"] == 0 else d["envs_per_cta"]
         return d
 
     def algorithmic_bytes_per_step(self, mean_sum_len):

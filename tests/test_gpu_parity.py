@@ -273,3 +273,20 @@ def test_shard_invariance(sb):
         assert abs(sw[k] - (sa[k] + sb_[k])) < 1e-6
     for e in (whole, a_env, b_env):
         e.close()
+
+
+@pytest.mark.parametrize("variant", ["ws", "split"])
+def test_lane_kernel_variants_match_oracle(sb, monkeypatch, variant):
+    """The alternative forms of the lane path (warp-specialised single kernel; logic + paint as two
+    kernels) produce the same bytes as the default fused form."""
+    monkeypatch.setenv("SNK_LANE", variant)
+    for rules, S, D, N, steps in (("classic", 2, 19, 1000, 120), ("adversarial", 3, 10, 300, 150), ("cut", 3, 10, 300, 150)):
+        kw = dict(size=D, n_snakes=S, rules=rules, seed=13)
+        env = sb.SnakeVecEnv(N, **kw)
+        co = c_oracle.COracle(N, **kw)
+        assert np.array_equal(env.reset().cpu().numpy(), co.reset())
+        for t in range(steps):
+            a = c_oracle.gen_actions(co.cfg, t, 5, env.action_space.n)
+            _compare_step(env, co, a, "%s %s step %d" % (variant, rules, t), check_state=(t % 10 == 0))
+        env.close()
+    monkeypatch.delenv("SNK_LANE")

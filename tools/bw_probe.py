@@ -1,0 +1,23 @@
+"""HBM ceilings on this box for the access pattern of the env step (pure streaming write)."""
+import torch
+def timeit(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(n):
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+for mb in (347, 1024, 2776):
+    nbytes = mb * 1000 * 1000 // 16 * 16
+    a = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    b = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    t = timeit(lambda: a.zero_())
+    print("fill  %5d MB: %.1f us  %.0f GB/s (write only)" % (mb, t * 1e3, nbytes / t / 1e6))
+    t = timeit(lambda: a.view(torch.int32).fill_(7))
+    print("fill32 %4d MB: %.1f us  %.0f GB/s (write only)" % (mb, t * 1e3, nbytes / t / 1e6))
+    t = timeit(lambda: b.copy_(a))
+    print("copy  %5d MB: %.1f us  %.0f GB/s (read+write)" % (mb, t * 1e3, 2 * nbytes / t / 1e6))
+    t = timeit(lambda: torch.cuda.memset if False else a.view(torch.int64).sum())
+    print("read  %5d MB: %.1f us  %.0f GB/s (read only)" % (mb, t * 1e3, nbytes / t / 1e6))
