@@ -25,6 +25,28 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, u32
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// global -> shared bulk copy completing on an mbarrier (used once per warp to fetch the border image)
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (u32)__cvta_generic_to_shared(sdst)),
+               "l"((u64)__cvta_generic_to_global(gsrc)), "r"(bytes), "r"((u32)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"((u32)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void flush_stats(const Params& p, const WarpStats& st, u32 errs, double* s_stats, int lane) {
@@ -220,9 +242,10 @@ __global__ void __launch_bounds__(128) k_lane_logic(const Params p) {
     LaneRng rng;
     rng.have = false; rng.blk = 0;
     u8* grid = p.grid ? p.grid + e * p.grid_stride : nullptr;
-    lane_load<S>(p, e, env);
+    const LaneRaw<S> raw = lane_fetch<S>(p, e, p.mode == MODE_STEP);
+    lane_unpack<S>(raw, env);
     if (p.mode == MODE_STEP) {
-      lane_step<S, RULES>(p, e, env, rng, grid, errs, st);
+      lane_step<S, RULES>(p, e, env, raw.act, rng, grid, errs, st);
     } else if (!p.mask || p.mask[e]) {
       lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);
     }
@@ -331,9 +354,10 @@ __global__ void __launch_bounds__(160, 5) k_step_lane_ws(const Params p) {
         LaneRng rng;
         rng.have = false; rng.blk = 0;
         u8* grid = p.grid ? p.grid + e * p.grid_stride : nullptr;
-        lane_load<S>(p, e, env);
+        const LaneRaw<S> raw = lane_fetch<S>(p, e, p.mode == MODE_STEP);
+        lane_unpack<S>(raw, env);
         if (p.mode == MODE_STEP) {
-          lane_step<S, RULES>(p, e, env, rng, grid, errs, st);
+          lane_step<S, RULES>(p, e, env, raw.act, rng, grid, errs, st);
         } else if (!p.mask || p.mask[e]) {
           lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);
         }
@@ -356,11 +380,17 @@ template <int S, int RULES, int K>
 __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   extern __shared__ __align__(128) u8 smem[];
   __shared__ double s_stats[SNK_NSTATS];
+  __shared__ __align__(8) u64 s_bar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
   const int TE = p.TE, LPE = 32 / TE, E = p.E;
   const int tile_bytes = TE * E;
   u8* tile = smem + warp * p.tile_stride;
-  init_border_image(p, tile, lane);
+  // the border-only image arrives through the TMA engine while the first batch is being stepped
+  if (lane == 0) {
+    mbar_init(&s_bar[warp], 1);
+    mbar_expect_tx(&s_bar[warp], (u32)tile_bytes);
+    for (int c = 0; c < TE / p.G; ++c) bulk_load_g2s(tile + c * p.G * E, p.tmpl, (u32)(p.G * E), &s_bar[warp]);
+  }
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
   __syncthreads();
   LaneStats st = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -368,7 +398,13 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   const int slot = lane / LPE, sub = lane - slot * LPE;
   u8* img = tile + slot * E;
   const long long n_batches = (p.N + 31) / 32;
-  for (long long b = (long long)blockIdx.x * wpc + warp; b < n_batches; b += (long long)gridDim.x * wpc) {
+  const long long stride = (long long)gridDim.x * wpc;
+  const bool stepping = p.mode == MODE_STEP;
+  long long b = (long long)blockIdx.x * wpc + warp;
+  LaneRaw<S> raw;
+  if (b < n_batches && b * 32 + lane < p.N) raw = lane_fetch<S>(p, b * 32 + lane, stepping);
+  bool have_image = false;
+  for (; b < n_batches; b += stride) {
     const long long e = b * 32 + lane;
     const bool valid = e < p.N;
     LaneEnv<S> env;
@@ -379,14 +415,17 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
       LaneRng rng;
       rng.have = false; rng.blk = 0;
       u8* grid = p.grid ? p.grid + e * p.grid_stride : nullptr;
-      lane_load<S>(p, e, env);
-      if (p.mode == MODE_STEP) {
-        lane_step<S, RULES>(p, e, env, rng, grid, errs, st);
+      lane_unpack<S>(raw, env);
+      if (stepping) {
+        lane_step<S, RULES>(p, e, env, raw.act, rng, grid, errs, st);
       } else if (p.mode == MODE_RESET) {
         if (!p.mask || p.mask[e]) lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);
       }
       if (p.mode != MODE_OBSERVE) lane_store<S>(p, e, env);
     }
+    // records + actions of this warp's NEXT batch: in flight while the current one is painted
+    if (b + stride < n_batches && (b + stride) * 32 + lane < p.N) raw = lane_fetch<S>(p, (b + stride) * 32 + lane, stepping);
+    if (!have_image) { mbar_wait(&s_bar[warp], 0); have_image = true; }
     __syncwarp();  // chain words / fruit grid written by the owner lane are read by the painting lanes
     for (int q = 0; q < LPE; ++q) {
       const long long e0 = b * 32 + (long long)q * TE;
@@ -401,6 +440,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
       __syncwarp();
     }
   }
+  if (!have_image) mbar_wait(&s_bar[warp], 0);  // never leave with a bulk copy into our shared memory in flight
   if (lane == 0) bulk_wait_all();
   reduce_lane_stats(p, st, errs, s_stats, lane);
   __syncthreads();

@@ -144,15 +144,13 @@ struct LaneStats {
 
 // One env step in one lane (:166-197).
 template <int S, int RULES>
-__device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, u8* grid, u32& errs, LaneStats& st) {
+__device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<S>& env, u32 act_packed, LaneRng& rng, u8* grid,
+                                          u32& errs, LaneStats& st) {
   const int V = p.V, F = p.F;
   const u32* chain_e = p.chain + e * S * p.CW;
   int act[S];
-  {
-    const int8_t* a = p.actions + e * S;
 #pragma unroll
-    for (int s = 0; s < S; ++s) act[s] = a[s];
-  }
+  for (int s = 0; s < S; ++s) act[s] = (int)(int8_t)(act_packed >> (8 * s));
   u32 was_alive = 0, moved = 0, strike = 0;
   int eaten[S];
   // ---- update_snake for every snake in index order (:97-145)
@@ -294,13 +292,40 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<
   }
 }
 
+// The record and the actions of one env as they sit in HBM: fetched early (the loads stay in flight
+// while the warp paints the previous batch) and unpacked when the step starts.
 template <int S>
-__device__ __forceinline__ void lane_load(const Params& p, long long e, LaneEnv<S>& env) {
+struct LaneRaw {
+  uint4 v[LaneRec<S>::RW / 4];
+  u32 act;  // S int8 actions, little-endian
+};
+
+template <int S>
+__device__ __forceinline__ LaneRaw<S> lane_fetch(const Params& p, long long e, bool with_actions) {
   constexpr int RW = LaneRec<S>::RW;
-  u32 r[RW];
+  LaneRaw<S> raw;
   const uint4* g = reinterpret_cast<const uint4*>(p.rec + e * RW);
 #pragma unroll
-  for (int i = 0; i < RW / 4; ++i) { const uint4 v = g[i]; r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w; }
+  for (int i = 0; i < RW / 4; ++i) raw.v[i] = g[i];
+  raw.act = 0;
+  if (with_actions) {
+    const int8_t* a = p.actions + e * S;
+    if (S == 2) raw.act = *reinterpret_cast<const u16*>(a);
+    else if (S == 4) raw.act = *reinterpret_cast<const u32*>(a);
+    else {
+#pragma unroll
+      for (int s = 0; s < S; ++s) raw.act |= (u32)(u8)a[s] << (8 * s);
+    }
+  }
+  return raw;
+}
+
+template <int S>
+__device__ __forceinline__ void lane_unpack(const LaneRaw<S>& raw, LaneEnv<S>& env) {
+  constexpr int RW = LaneRec<S>::RW;
+  u32 r[RW];
+#pragma unroll
+  for (int i = 0; i < RW / 4; ++i) { r[4 * i] = raw.v[i].x; r[4 * i + 1] = raw.v[i].y; r[4 * i + 2] = raw.v[i].z; r[4 * i + 3] = raw.v[i].w; }
   env.t = r[REC_T]; env.ep_len = r[REC_EP_LEN]; env.ctr = r[REC_DRAW_CTR]; env.ep_ret = __uint_as_float(r[REC_EP_RET]);
   env.spare = r[REC_SPARE];
 #pragma unroll
@@ -311,6 +336,12 @@ __device__ __forceinline__ void lane_load(const Params& p, long long e, LaneEnv<
   }
   env.fruit[0] = r[REC_SNAKE0 + 2 * S] & 0xffff; env.fruit[1] = r[REC_SNAKE0 + 2 * S] >> 16;
   env.fruit[2] = r[REC_SNAKE0 + 2 * S + 1] & 0xffff; env.fruit[3] = r[REC_SNAKE0 + 2 * S + 1] >> 16;
+}
+
+template <int S>
+__device__ __forceinline__ void lane_load(const Params& p, long long e, LaneEnv<S>& env) {
+  const LaneRaw<S> raw = lane_fetch<S>(p, e, false);
+  lane_unpack<S>(raw, env);
 }
 
 template <int S>
