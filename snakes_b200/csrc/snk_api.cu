@@ -170,6 +170,11 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   p.family = plan.kind == KIND_LANE;
   { const char* sm = getenv("SNK_STORE"); p.store_mode = (sm && !strcmp(sm, "stg")) ? 1 : 0; }
   { const char* dbg = getenv("SNK_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+  {  // L2 policies (SNK_L2 = bit0 obs evict-first, bit1 records evict-last; testing aid)
+    const char* l2 = getenv("SNK_L2");
+    const int bits = l2 ? atoi(l2) : 3;
+    p.obs_evict_first = bits & 1; p.rec_evict_last = (bits >> 1) & 1;
+  }
   int logic_warps = 3;
   // lane path variants (SNK_LANE=fused|ws|split, testing aid): every warp steps 32 envs then streams
   // their images (default: fastest measured), warp-specialised single kernel, or two kernels

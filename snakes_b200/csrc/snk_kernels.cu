@@ -22,6 +22,19 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, u32
   const u64 g = (u64)__cvta_generic_to_global(gdst);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"(s), "r"(bytes) : "memory");
 }
+// same, with an L2 evict-first policy: the observation stream is write-once and larger than L2, so
+// it should not push the (re-read every step) env records out of the cache
+__device__ __forceinline__ u64 l2_evict_first_policy() {
+  u64 pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_store_s2g_hint(void* gdst, const void* ssrc, u32 bytes, u64 pol) {
+  const u32 s = (u32)__cvta_generic_to_shared(ssrc);
+  const u64 g = (u64)__cvta_generic_to_global(gdst);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(g), "r"(s), "r"(bytes), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -182,8 +195,14 @@ __device__ __forceinline__ void store_image(const Params& p, const u8* tile, int
   u8* gdst = p.obs + e0 * (long long)p.E;
   if (left >= p.TE && p.store_mode == 0) {
     if (lane == 0) {
-      for (int off = 0; off < tile_bytes; off += 16384)
-        bulk_store_s2g(gdst + off, tile + off, (u32)min(16384, tile_bytes - off));
+      if (!p.obs_evict_first) {
+        for (int off = 0; off < tile_bytes; off += 16384)
+          bulk_store_s2g(gdst + off, tile + off, (u32)min(16384, tile_bytes - off));
+      } else {
+        const u64 pol = l2_evict_first_policy();
+        for (int off = 0; off < tile_bytes; off += 16384)
+          bulk_store_s2g_hint(gdst + off, tile + off, (u32)min(16384, tile_bytes - off), pol);
+      }
       bulk_commit();
       bulk_wait_read();
     }

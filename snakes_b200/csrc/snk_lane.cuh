@@ -305,8 +305,17 @@ __device__ __forceinline__ LaneRaw<S> lane_fetch(const Params& p, long long e, b
   constexpr int RW = LaneRec<S>::RW;
   LaneRaw<S> raw;
   const uint4* g = reinterpret_cast<const uint4*>(p.rec + e * RW);
+  if (p.rec_evict_last) {  // keep the records L2-resident across steps (they are re-read by the next launch)
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
 #pragma unroll
-  for (int i = 0; i < RW / 4; ++i) raw.v[i] = g[i];
+    for (int i = 0; i < RW / 4; ++i)
+      asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                   : "=r"(raw.v[i].x), "=r"(raw.v[i].y), "=r"(raw.v[i].z), "=r"(raw.v[i].w) : "l"(g + i), "l"(pol));
+  } else {
+#pragma unroll
+    for (int i = 0; i < RW / 4; ++i) raw.v[i] = g[i];
+  }
   raw.act = 0;
   if (with_actions) {
     const int8_t* a = p.actions + e * S;
@@ -361,8 +370,17 @@ __device__ __forceinline__ void lane_store(const Params& p, long long e, const L
   r[REC_SNAKE0 + 2 * S] = (u32)env.fruit[0] | ((u32)env.fruit[1] << 16);
   r[REC_SNAKE0 + 2 * S + 1] = (u32)env.fruit[2] | ((u32)env.fruit[3] << 16);
   uint4* g = reinterpret_cast<uint4*>(p.rec + e * RW);
+  if (p.rec_evict_last) {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
 #pragma unroll
-  for (int i = 0; i < RW / 4; ++i) g[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    for (int i = 0; i < RW / 4; ++i)
+      asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(g + i), "r"(r[4 * i]), "r"(r[4 * i + 1]),
+                   "r"(r[4 * i + 2]), "r"(r[4 * i + 3]), "l"(pol) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < RW / 4; ++i) g[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+  }
 }
 
 // Position of segment i without walking: the 2-bit codes before it are counted per direction with
