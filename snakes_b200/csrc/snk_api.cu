@@ -163,8 +163,19 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   }
   const int W = p.G > 8 ? p.G : 8;
   const size_t smem_tile = (size_t)(W + p.G) * p.E + (size_t)W * (REC_SNAKE0 + 2 * S + (F + 1) / 2 + 3 + p.bm_words) * 4;
-  plan.kind = TE ? KIND_LANE : smem_tile <= 110 * 1024 ? KIND_TILE : KIND_DENSE;
+  // rows kernel: chunks of R image rows must be 16-byte multiples (TMA) and fit a ~24 KB buffer
+  int R = 0;
+  if (p.E % 16 == 0) {
+    const int unit = 16 / gcd(V * p.C, 16);
+    { const char* rk = getenv("SNK_ROWS_KB"); const size_t lim = (size_t)(rk ? atoi(rk) : 12) * 1024;
+      for (int r = unit; r <= V && ((size_t)r * V * p.C <= lim || !R); r += unit) { if ((size_t)r * V * p.C > 48 * 1024) break; R = r; } }
+  }
+  plan.kind = TE ? KIND_LANE : smem_tile <= 110 * 1024 ? KIND_TILE : R ? KIND_ROWS : KIND_DENSE;
   if (force && !strcmp(force, "dense")) plan.kind = KIND_DENSE;
+  if (force && !strcmp(force, "rows")) {
+    if (!R) { snk_destroy(h); return fail(SNK_EINVAL, "rows kernel does not support this configuration"); }
+    plan.kind = KIND_ROWS;
+  }
   if (force && !strcmp(force, "tile") && smem_tile <= 200 * 1024) plan.kind = KIND_TILE;
   if (force && !strcmp(force, "lane") && !TE) { snk_destroy(h); return fail(SNK_EINVAL, "lane kernel does not support this configuration"); }
   p.family = plan.kind == KIND_LANE;
@@ -198,6 +209,11 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   } else if (plan.kind == KIND_TILE) {
     p.W = W; plan.block = 32 * W; plan.smem = smem_tile;
     p.n_groups = (N + W - 1) / W;
+  } else if (plan.kind == KIND_ROWS) {
+    p.W = 1; p.R = R; { const char* rb = getenv("SNK_ROWS_BLOCK"); plan.block = rb ? atoi(rb) : (cfg->rules == SNK_RULES_CLASSIC ? 128 : 64); }
+    p.tile_stride = (int)(((size_t)R * V * p.C + 127) & ~(size_t)127);
+    plan.smem = (((size_t)p.VV + 127) & ~(size_t)127) + 2 * (size_t)p.tile_stride + (size_t)(p.RW + p.bm_words) * 4;
+    p.n_groups = N;
   } else {
     p.W = 1; plan.block = 256; plan.smem = align16((size_t)p.VV) + (size_t)(p.RW + p.bm_words) * 4;
     p.n_groups = N;

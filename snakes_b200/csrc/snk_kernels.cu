@@ -520,6 +520,115 @@ __global__ void __launch_bounds__(256) k_step_dense(const Params p) {
   if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
+
+// k_step_rows: large fields (e.g. 16 snakes on 64x64: 209 KB of observation per env).  One CTA per
+// env: warp 0 runs the warp-cooperative logic, all threads build the cell-code grid in shared
+// memory (fruits, snakes in index order, border: the reference's paint order, get_ob_for_snake
+// :35-58), then the image leaves in chunks of R rows: each thread expands whole pixels (one code ->
+// 3K bytes, written once, 16-byte vector stores) into one of two chunk buffers and a TMA bulk copy
+// streams the buffer out while the next chunk is being expanded.
+__device__ __forceinline__ void pattern3(u32 rgb, u32& w0, u32& w1, u32& w2) {  // RGBRGB... as 3 periodic words
+  const u32 r = rgb & 255, g = (rgb >> 8) & 255, b = (rgb >> 16) & 255;
+  w0 = r | g << 8 | b << 16 | r << 24; w1 = g | b << 8 | r << 16 | g << 24; w2 = b | r << 8 | g << 16 | b << 24;
+}
+
+template <int RULES>
+__global__ void __launch_bounds__(256) k_step_rows(const Params p) {
+  extern __shared__ __align__(128) u8 smem[];
+  __shared__ double s_stats[SNK_NSTATS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  const int S = p.S, F = p.F, K = p.K, C = p.C, VV = p.VV, V = p.V, cap = p.cap, R = p.R;
+  u8* code = smem;  // [VV] 0 empty, 1 fruit, 3+2s body of s, 4+2s head of s, 255 border
+  u8* tiles = smem + ((VV + 127) & ~127);
+  u32* sc = reinterpret_cast<u32*>(tiles + 2 * p.tile_stride);
+  u32* bm = sc + p.RW;
+  if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  __syncthreads();
+  WarpStats st = {0, 0, 0, 0, 0, 0, 0, 0};
+  u32 errs = 0;
+  const int n_chunks = (V + R - 1) / R;
+  int issued = 0;  // chunks handed to the TMA engine so far (thread 0's bulk groups)
+  for (long long e = blockIdx.x; e < p.N; e += gridDim.x) {
+    if (warp == 0) advance_env<RULES>(p, e, lane, sc, bm, errs, st);
+    for (int i = tid; i < VV; i += nthr) code[i] = 0;
+    __syncthreads();
+    // Codes grow in paint order (fruit 1 < snake s body 3+2s < head 4+2s < border 255), so "a later
+    // item overwrites an earlier one" is a per-cell MAX.  All snakes are painted at once; a pass is
+    // repeated until no thread had to raise a cell (cells shared by two snakes are rare).
+    if (RULES == SNK_RULES_CLASSIC) {
+      const u16* fr = reinterpret_cast<const u16*>(sc + REC_SNAKE0 + 2 * S);
+      if (tid < F) code[fr[tid]] = 1;
+    } else {
+      const u8* grid = p.grid + e * p.grid_stride;
+      for (int i = tid; i < VV; i += nthr) if (grid[i]) code[i] = 1;
+    }
+    __syncthreads();
+    const u16* rings = p.body + e * S * cap;
+    for (int pass = 0; pass < 64; ++pass) {
+      int changed = 0;
+      for (int s = 0; s < S; ++s) {
+        const u32 a = sc[REC_SNAKE0 + 2 * s];
+        const int len = a >> 16, hs = a & 0xffff;
+        for (int i = tid; i < len; i += nthr) {
+          const int cell = ring_at(rings + s * cap, hs, i, cap);
+          const u8 mine = (u8)(3 + 2 * s + (i == 0));
+          if (code[cell] < mine) { code[cell] = mine; changed = 1; }
+        }
+      }
+      if (!__syncthreads_or(changed)) break;
+    }
+    for (int i = tid; i < V; i += nthr) { code[i] = 255; code[(V - 1) * V + i] = 255; code[i * V] = 255; code[i * V + V - 1] = 255; }
+    __syncthreads();
+    u8* out = p.obs + e * (long long)p.E;
+    for (int c = 0; c < n_chunks; ++c) {
+      u8* tile = tiles + (issued & 1) * p.tile_stride;
+      if (issued >= 2) {  // the copy that last used this buffer has been read by the engine
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+      }
+      const int r0 = c * R, rows = min(R, V - r0), cells = rows * V;
+      for (int i = tid; i < cells; i += nthr) {
+        const int cd = code[r0 * V + i];
+        u32 rgb = 0;
+        int self = -1;
+        if (cd == 1) rgb = 255u;
+        else if (cd == 255) rgb = 0xffffffu;
+        else if (cd >= 3) { self = (cd - 3) >> 1; rgb = snake_rgb(false, (cd - 3) & 1); }
+        u32 w0, w1, w2;
+        pattern3(rgb, w0, w1, w2);
+        u8* px = tile + i * C;
+        if ((C & 15) == 0) {
+          uint4* q = reinterpret_cast<uint4*>(px);
+          for (int j = 0; j < C / 16; ++j) {  // word index 4j: period 3 words
+            const int ph = (4 * j) % 3;
+            const u32 a0 = ph == 0 ? w0 : ph == 1 ? w1 : w2, a1 = ph == 0 ? w1 : ph == 1 ? w2 : w0, a2 = ph == 0 ? w2 : ph == 1 ? w0 : w1;
+            q[j] = make_uint4(a0, a1, a2, a0);
+          }
+        } else {
+          for (int j = 0; j < C; ++j) px[j] = (u8)(rgb >> (8 * (j % 3)));
+        }
+        if (self >= 0 && self < K) {
+          const u32 own = snake_rgb(true, (cd - 3) & 1);
+          px[3 * self] = (u8)own; px[3 * self + 1] = (u8)(own >> 8); px[3 * self + 2] = (u8)(own >> 16);
+        }
+      }
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        const int bytes = cells * C;
+        for (int off = 0; off < bytes; off += 16384)
+          bulk_store_s2g(out + (long long)r0 * V * C + off, tile + off, (u32)min(16384, bytes - off));
+        bulk_commit();
+      }
+      ++issued;
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+  if (warp == 0) flush_stats(p, st, errs, s_stats, lane);
+  __syncthreads();
+  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+}
+
 // ------------------------------------------------------------------ state dump / load, action stream
 // canonical blob <-> private layout; one thread per (env, snake); not on the hot path
 __global__ void k_dump(const Params p, u8* blob, snk_state_layout lay) {
@@ -641,6 +750,10 @@ static cudaError_t launch_rules(const Params& p, const LaunchPlan& plan, cudaStr
 #undef X
     return cudaErrorInvalidConfiguration;
   }
+  if (plan.kind == KIND_ROWS) {
+    k_step_rows<RULES><<<plan.grid, plan.block, plan.smem, stream>>>(p);
+    return cudaGetLastError();
+  }
   if (plan.kind == KIND_TILE) {
     if (plan.block <= 256) k_step_tile<RULES, 256><<<plan.grid, plan.block, plan.smem, stream>>>(p);
     else k_step_tile<RULES, 512><<<plan.grid, plan.block, plan.smem, stream>>>(p);
@@ -682,6 +795,9 @@ static cudaError_t plan_rules(LaunchPlan& plan, int n_sm, int S, int K) {
     LANE_COMBOS(X)
 #undef X
     if (err) return err;
+  } else if (plan.kind == KIND_ROWS) {
+    if ((err = cudaFuncSetAttribute(k_step_rows<RULES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
+    if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_rows<RULES>, plan.block, plan.smem))) return err;
   } else if (plan.kind == KIND_TILE && plan.block <= 256) {
     if ((err = cudaFuncSetAttribute(k_step_tile<RULES, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
     if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_tile<RULES, 256>, plan.block, plan.smem))) return err;

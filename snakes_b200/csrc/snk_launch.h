@@ -6,10 +6,10 @@
 #include "../../include/snk.h"
 
 struct Params;
-enum { KIND_LANE = 0, KIND_TILE = 1, KIND_DENSE = 2 };
+enum { KIND_LANE = 0, KIND_TILE = 1, KIND_DENSE = 2, KIND_ROWS = 3 };
 
 struct LaunchPlan {
-  int kind;         // KIND_LANE (lane per env, chain bodies), KIND_TILE (warp per env) or KIND_DENSE (CTA per env)
+  int kind;         // KIND_LANE (lane per env, chain bodies), KIND_TILE (warp per env), KIND_ROWS / KIND_DENSE (CTA per env)
   bool ws;          // lane path as ONE warp-specialised kernel (k_step_lane_ws): paint warps + logic warps per CTA
   bool split;       // lane path as two kernels: k_lane_logic (thread per env) + k_lane_paint (observation writer)
   int grid, block;

@@ -287,7 +287,7 @@ class SnakeVecEnv(object):
         out = (C.c_int32 * 6)()
         _lib.check(self._L.snk_launch_info(self._h, out))
         d = dict(zip(("kind", "grid", "block", "smem", "occupancy", "envs_per_cta"), list(out)))
-        d["kernel"] = ("k_step_lane", "k_step_tile", "k_step_dense")[d["kind"]]
+        d["kernel"] = ("k_step_lane", "k_step_tile", "k_step_dense", "k_step_rows")[d["kind"]]
         d["envs_per_cta"] = d["block"] if d["kind"] == 0 else d["envs_per_cta"]
         return d
 

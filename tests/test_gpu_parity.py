@@ -187,6 +187,22 @@ def test_known_answers(sb):
         env.close()
 
 
+def test_rows_kernel_small_fields(sb, monkeypatch):
+    """The row-chunked CTA-per-env kernel forced onto boards whose rows are 16-byte multiples."""
+    monkeypatch.setenv("SNK_FORCE_KERNEL", "rows")
+    for rules, S, D, K, N, steps in (("classic", 4, 14, 4, 60, 150), ("cut", 4, 30, 4, 40, 150), ("adversarial", 3, 10, 4, 50, 150)):
+        kw = dict(size=D, n_snakes=S, n_views=K, rules=rules, seed=19)
+        env = sb.SnakeVecEnv(N, **kw)
+        assert env.launch_info()["kernel"] == "k_step_rows"
+        co = c_oracle.COracle(N, **kw)
+        assert np.array_equal(env.reset().cpu().numpy(), co.reset())
+        for t in range(steps):
+            a = c_oracle.gen_actions(co.cfg, t, 5, env.action_space.n)
+            _compare_step(env, co, a, "rows %s step %d" % (rules, t), check_state=(t % 10 == 0))
+        env.close()
+    monkeypatch.delenv("SNK_FORCE_KERNEL")
+
+
 @pytest.mark.parametrize("kernel", ["tile", "dense"])
 def test_general_kernels_match_oracle(sb, monkeypatch, kernel):
     """The warp-per-env tile kernel and the CTA-per-env dense kernel (used for boards outside the
