@@ -233,6 +233,8 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   if (p.family == 1) TRY(dev_alloc(h, &p.chain, (size_t)N * S * p.CW, true));
   else TRY(dev_alloc(h, &p.body, (size_t)N * S * p.cap, true));
   if (cfg->rules != SNK_RULES_CLASSIC) TRY(dev_alloc(h, &p.grid, (size_t)N * p.grid_stride, true));
+  p.GBW = (p.VV + 31) / 32;
+  if (cfg->rules != SNK_RULES_CLASSIC && p.family == 1) TRY(dev_alloc(h, &p.gbits, (size_t)N * p.GBW, true));
   TRY(dev_alloc(h, &h->d_obs_own, (size_t)N * p.E, true));
   p.obs = h->d_obs_own;
   TRY(dev_alloc(h, &p.reward, (size_t)N, true));

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(128) k_lane_logic(const Params p) {
     LaneEnv<S> env;
     LaneRng rng;
     rng.have = false; rng.blk = 0;
-    u8* grid = p.grid ? p.grid + e * p.grid_stride : nullptr;
+    const FruitSet grid = fruit_set(p, e);
     const LaneRaw<S> raw = lane_fetch<S>(p, e, p.mode == MODE_STEP);
     lane_unpack<S>(raw, env);
     if (p.mode == MODE_STEP) {
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(160, 5) k_step_lane_ws(const Params p) {
         LaneEnv<S> env;
         LaneRng rng;
         rng.have = false; rng.blk = 0;
-        u8* grid = p.grid ? p.grid + e * p.grid_stride : nullptr;
+        const FruitSet grid = fruit_set(p, e);
         const LaneRaw<S> raw = lane_fetch<S>(p, e, p.mode == MODE_STEP);
         lane_unpack<S>(raw, env);
         if (p.mode == MODE_STEP) {
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
     if (valid) {
       LaneRng rng;
       rng.have = false; rng.blk = 0;
-      u8* grid = p.grid ? p.grid + e * p.grid_stride : nullptr;
+      const FruitSet grid = fruit_set(p, e);
       lane_unpack<S>(raw, env);
       if (stepping) {
         lane_step<S, RULES>(p, e, env, raw.act, rng, grid, errs, st);
@@ -659,7 +659,10 @@ __global__ void k_dump(const Params p, u8* blob, snk_state_layout lay) {
     reinterpret_cast<u32*>(blob + lay.off_draw_ctr)[e] = r[REC_DRAW_CTR];
     reinterpret_cast<u32*>(blob + lay.off_ep_ret)[e] = r[REC_EP_RET];
     reinterpret_cast<int32_t*>(blob + lay.off_ep_len)[e] = (int32_t)r[REC_EP_LEN];
-    if (lay.fruit_is_grid) {
+    if (lay.fruit_is_grid && p.family == 1) {
+      for (int k = 0; k < p.VV; ++k)
+        (blob + lay.off_fruit)[e * p.VV + k] = ((p.gbits[e * p.GBW + (k >> 5)] >> (k & 31)) & 1) ? p.grid[e * p.grid_stride + k] : (u8)0;
+    } else if (lay.fruit_is_grid) {
       for (int k = 0; k < p.VV; ++k) (blob + lay.off_fruit)[e * p.VV + k] = p.grid[e * p.grid_stride + k];
     } else {
       const u16* fr = reinterpret_cast<const u16*>(r + REC_SNAKE0 + 2 * S);
@@ -705,6 +708,13 @@ __global__ void k_load(const Params p, const u8* blob, snk_state_layout lay) {
     if (p.family == 0) r[5] = r[6] = r[7] = 0;
     if (lay.fruit_is_grid) {
       for (int k = 0; k < p.VV; ++k) p.grid[e * p.grid_stride + k] = (blob + lay.off_fruit)[e * p.VV + k];
+      if (p.family == 1) {
+        for (int w = 0; w < p.GBW; ++w) {
+          u32 bits = 0;
+          for (int k = 32 * w; k < min(32 * w + 32, p.VV); ++k) if (p.grid[e * p.grid_stride + k]) bits |= 1u << (k & 31);
+          p.gbits[e * p.GBW + w] = bits;
+        }
+      }
     } else {
       u16* fr = reinterpret_cast<u16*>(r + REC_SNAKE0 + 2 * S);
       for (int k = 0; k < p.F; ++k) fr[k] = reinterpret_cast<const u16*>(blob + lay.off_fruit)[e * p.F + k];

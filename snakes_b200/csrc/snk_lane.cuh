@@ -112,13 +112,45 @@ __device__ __forceinline__ int lane_spawn(const Params& p, long long e, LaneEnv<
   return p.V + 1;
 }
 
+
+// Fruit multiset of the adversarial / cut rule-sets in the lane family: `gbits` holds one bit per
+// padded cell (set = at least one fruit), `grid` the count, VALID ONLY WHERE THE BIT IS SET.  Reset
+// therefore clears GBW words instead of V*V bytes and painting scans GBW words instead of the grid.
+struct FruitSet {
+  u8* cnt;    // [VV]
+  u32* bits;  // [GBW]
+};
+__device__ __forceinline__ FruitSet fruit_set(const Params& p, long long e) {
+  FruitSet f;
+  f.cnt = p.grid ? p.grid + e * p.grid_stride : nullptr;
+  f.bits = p.gbits ? p.gbits + e * p.GBW : nullptr;
+  return f;
+}
+__device__ __forceinline__ int fruit_count(const FruitSet& f, int pid) {
+  return ((f.bits[pid >> 5] >> (pid & 31)) & 1) ? (int)f.cnt[pid] : 0;
+}
+__device__ __forceinline__ void fruit_inc(const FruitSet& f, int pid, u32& errs) {
+  const u32 w = f.bits[pid >> 5], m = 1u << (pid & 31);
+  if (w & m) {
+    const u8 c = f.cnt[pid];
+    if (c == 255) errs |= SNK_DEVERR_FRUIT_OVERFLOW; else f.cnt[pid] = c + 1;
+  } else {
+    f.cnt[pid] = 1;
+    f.bits[pid >> 5] = w | m;
+  }
+}
+__device__ __forceinline__ void fruit_dec(const FruitSet& f, int pid) {
+  const u8 c = f.cnt[pid] - 1;
+  f.cnt[pid] = c;
+  if (c == 0) f.bits[pid >> 5] &= ~(1u << (pid & 31));
+}
+
 // reset (:219-232): snake_i.x, snake_i.y, fruit_i.x, fruit_i.y interleaved, randint(D) each
 template <int S, int RULES>
-__device__ __forceinline__ void lane_reset(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, u8* grid, u32& errs, float& draws) {
+__device__ __forceinline__ void lane_reset(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, const FruitSet& fs, u32& errs, float& draws) {
   const int F = p.F, V = p.V;
   if (RULES != SNK_RULES_CLASSIC) {
-    u32* g32 = reinterpret_cast<u32*>(grid);
-    for (int w = 0; w < p.grid_stride / 4; ++w) g32[w] = 0;
+    for (int w = 0; w < p.GBW; ++w) fs.bits[w] = 0;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -132,7 +164,7 @@ __device__ __forceinline__ void lane_reset(const Params& p, long long e, LaneEnv
       const int x = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
       const int y = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
       const int pid = (x + 1) * V + (y + 1);
-      if (RULES == SNK_RULES_CLASSIC) env.fruit[i] = pid; else grid_inc(grid, pid, errs);
+      if (RULES == SNK_RULES_CLASSIC) env.fruit[i] = pid; else fruit_inc(fs, pid, errs);
     }
   }
   env.t = 0; env.ep_len = 0; env.ep_ret = 0.f;  // `spare` survives (snake_adversarial_env.py:14)
@@ -144,7 +176,7 @@ struct LaneStats {
 
 // One env step in one lane (:166-197).
 template <int S, int RULES>
-__device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<S>& env, u32 act_packed, LaneRng& rng, u8* grid,
+__device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<S>& env, u32 act_packed, LaneRng& rng, const FruitSet& fs,
                                           u32& errs, LaneStats& st) {
   const int V = p.V, F = p.F;
   const u32* chain_e = p.chain + e * S * p.CW;
@@ -171,7 +203,7 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<
 #pragma unroll
       for (int f = 0; f < 4; ++f) if (f < F && env.fruit[f] == head) { hitmask |= 1u << f; ++n_eat; }   // :126-132
     } else {
-      n_eat = grid[head];
+      n_eat = fruit_count(fs, head);
     }
     const int grow = env.grow[s] + 2 * n_eat;
     int len = env.len[s];
@@ -198,7 +230,7 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<
           env.spare--;
         } else {
           const int cell = lane_spawn<S>(p, e, env, rng, errs, st.draws);
-          grid[head]--; grid_inc(grid, cell, errs);
+          fruit_dec(fs, head); fruit_inc(fs, cell, errs);
         }
       }
     }
@@ -244,7 +276,7 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<
             bool under = false;
 #pragma unroll
             for (int s = 0; s < S; ++s) under |= ((saved >> s) & 1) && pid == env.head[s];
-            if (!under) grid_inc(grid, pid, errs);
+            if (!under) fruit_inc(fs, pid, errs);
           });
           env.len[j] = cut; env.grow[j] = cut;
         }
@@ -255,7 +287,7 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<
 #pragma unroll
     for (int j = 0; j < S; ++j) {
       if (!((dead & ~empty) >> j & 1)) continue;
-      chain_walk(env.head[j], env.len[j], env.c0[j], chain_e + j * p.CW, V, [&](int, int pid) { grid_inc(grid, pid, errs); });
+      chain_walk(env.head[j], env.len[j], env.c0[j], chain_e + j * p.CW, V, [&](int, int pid) { fruit_inc(fs, pid, errs); });
       env.spare += (u32)(env.len[j] * env.len[j]);
     }
   }
@@ -288,7 +320,7 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<
   st.cells += (float)cells;
   if (done) {
     st.episodes += 1.f; st.ret_sum += env.ep_ret; st.len_sum += (float)env.ep_len;
-    if (p.auto_reset) lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);  // subproc_vec_env.py:13-16
+    if (p.auto_reset) lane_reset<S, RULES>(p, e, env, rng, fs, errs, st.draws);  // subproc_vec_env.py:13-16
   }
 }
 
@@ -479,12 +511,11 @@ __device__ __forceinline__ void lane_paint(const Params& p, const PaintEnv<S>& p
       }
     }
   } else if (pe.valid) {
-    const u32* g32 = reinterpret_cast<const u32*>(p.grid + e_owner * p.grid_stride);
-    for (int w = sub; w < (p.VV + 3) / 4; w += LPE) {
-      u32 word = g32[w];
-      for (int q = 0; word; ++q, word >>= 8) {
-        const int pid = 4 * w + q;
-        if ((word & 0xff) && pid < p.VV && !(__ldg(p.cellinfo + pid) >> 31)) {
+    const u32* gb = p.gbits + e_owner * p.GBW;
+    for (int w = sub; w < p.GBW; w += LPE) {
+      for (u32 bits = gb[w]; bits; bits &= bits - 1) {
+        const int pid = 32 * w + __ffs(bits) - 1;
+        if (!(__ldg(p.cellinfo + pid) >> 31)) {
 #pragma unroll
           for (int k = 0; k < K; ++k) img[pid * C + 3 * k] = PAINT ? 255 : 0;
         }
