@@ -32,7 +32,10 @@ struct snk_handle {
   Params p;
   LaunchPlan plan;
   int n_sm;
-  uint8_t* d_obs_own;
+  uint8_t* d_obs_own;     // native observations (the step kernels' output)
+  uint8_t* d_obs84_own;   // obs_mode atari84: the 84x84 images handed to the caller
+  uint8_t* d_obs_user;    // what snk_get_buffers reports: own buffer or the caller's target
+  size_t obs_out_env_bytes;
   int8_t* d_actions_own;
   uint8_t* d_blob;  // staging for dump / load
   uint32_t* d_tape_vals;
@@ -54,7 +57,11 @@ static int cfg_check(const snk_config* c) {
   if (c->rules < 0 || c->rules > 2) return fail(SNK_EINVAL, "unknown rules %d", c->rules);
   if (c->num_envs < 1) return fail(SNK_EINVAL, "num_envs must be >= 1");
   if (c->max_steps < 0 || c->max_steps > 65535) return fail(SNK_EINVAL, "max_steps must be 0..65535");
-  if (c->obs_mode != SNK_OBS_NATIVE) return fail(SNK_EINVAL, "obs_mode %d not supported yet (native only)", c->obs_mode);
+  if (c->obs_mode != SNK_OBS_NATIVE && c->obs_mode != SNK_OBS_ATARI84) return fail(SNK_EINVAL, "unknown obs_mode %d", c->obs_mode);
+  if (c->obs_mode == SNK_OBS_ATARI84 && 84 % (c->size + 2) != 0)
+    return fail(SNK_EINVAL, "obs_mode atari84 needs 84 %% (size + 2) == 0 (exact pixel replication); size=%d", c->size);
+  if (c->obs_mode == SNK_OBS_ATARI84 && (c->n_views ? c->n_views : c->n_snakes) > 8)
+    return fail(SNK_EINVAL, "obs_mode atari84 supports at most 8 views");
   if (c->rng_mode != SNK_RNG_PHILOX && c->rng_mode != SNK_RNG_TAPE) return fail(SNK_EINVAL, "unknown rng_mode %d", c->rng_mode);
   if ((uint64_t)(c->env_id_base + c->num_envs) > 0xffffffffull) return fail(SNK_EINVAL, "global env ids must fit 32 bits");
   return SNK_OK;
@@ -237,6 +244,14 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   if (cfg->rules != SNK_RULES_CLASSIC && p.family == 1) TRY(dev_alloc(h, &p.gbits, (size_t)N * p.GBW, true));
   TRY(dev_alloc(h, &h->d_obs_own, (size_t)N * p.E, true));
   p.obs = h->d_obs_own;
+  h->d_obs84_own = nullptr;
+  h->obs_out_env_bytes = (size_t)p.E;
+  h->d_obs_user = h->d_obs_own;
+  if (cfg->obs_mode == SNK_OBS_ATARI84) {
+    h->obs_out_env_bytes = (size_t)84 * 84 * p.C;
+    TRY(dev_alloc(h, &h->d_obs84_own, (size_t)N * h->obs_out_env_bytes, true));
+    h->d_obs_user = h->d_obs84_own;
+  }
   TRY(dev_alloc(h, &p.reward, (size_t)N, true));
   TRY(dev_alloc(h, &p.reward_all, (size_t)N * S, true));
   TRY(dev_alloc(h, &p.done, (size_t)N, true));
@@ -290,9 +305,10 @@ extern "C" int snk_get_config(const snk_handle* h, snk_config* out) {
 extern "C" int snk_get_buffers(const snk_handle* h, snk_buffers* out) {
   if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
   const Params& p = h->p;
-  out->d_obs = p.obs; out->d_reward = p.reward; out->d_reward_all = p.reward_all; out->d_done = p.done;
+  out->d_obs = h->d_obs_user; out->d_reward = p.reward; out->d_reward_all = p.reward_all; out->d_done = p.done;
   out->d_num_alive = p.num_alive; out->d_episode_return = p.fin_ret; out->d_episode_len = p.fin_len;
-  out->d_stats = p.stats; out->obs_bytes = (size_t)p.N * p.E; out->obs_h = p.V; out->obs_w = p.V; out->obs_c = p.C;
+  const int side = h->cfg.obs_mode == SNK_OBS_ATARI84 ? 84 : p.V;
+  out->d_stats = p.stats; out->obs_bytes = (size_t)p.N * h->obs_out_env_bytes; out->obs_h = side; out->obs_w = side; out->obs_c = p.C;
   return SNK_OK;
 }
 
@@ -304,6 +320,10 @@ static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_
   if (p.rng_mode == SNK_RNG_TAPE && !p.tape_vals) return fail(SNK_EINVAL, "rng_mode is TAPE but no tape was set");
   CUDA_TRY(snk_launch_step(p, h->cfg.rules, h->plan, stream));
   h->launches += (h->plan.split && mode != MODE_OBSERVE) ? 2 : 1;
+  if (h->cfg.obs_mode == SNK_OBS_ATARI84) {
+    CUDA_TRY(snk_launch_upscale84(p.obs, h->d_obs_user, p.N, p.V, p.C, h->n_sm, stream));
+    h->launches++;
+  }
   return SNK_OK;
 }
 
@@ -329,17 +349,24 @@ extern "C" int snk_step_host(snk_handle* h, const int8_t* h_actions, uint8_t* h_
   if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, p.reward, (size_t)p.N * 4, cudaMemcpyDeviceToHost, s));
   if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, p.done, (size_t)p.N, cudaMemcpyDeviceToHost, s));
   if (h_num_alive) CUDA_TRY(cudaMemcpyAsync(h_num_alive, p.num_alive, (size_t)p.N, cudaMemcpyDeviceToHost, s));
-  if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, p.obs, (size_t)p.N * p.E, cudaMemcpyDeviceToHost, s));
+  if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs_user, (size_t)p.N * h->obs_out_env_bytes, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return SNK_OK;
 }
 
 extern "C" int snk_set_obs_target(snk_handle* h, uint8_t* d_obs, size_t bytes) {
   if (!h) return fail(SNK_EINVAL, "handle is NULL");
-  if (!d_obs) { h->p.obs = h->d_obs_own; return SNK_OK; }
+  const bool atari = h->cfg.obs_mode == SNK_OBS_ATARI84;
+  if (!d_obs) {
+    h->d_obs_user = atari ? h->d_obs84_own : h->d_obs_own;
+    if (!atari) h->p.obs = h->d_obs_own;
+    return SNK_OK;
+  }
   if (((uintptr_t)d_obs & 15) != 0) return fail(SNK_EINVAL, "obs target must be 16-byte aligned");
-  if (bytes < (size_t)h->p.N * h->p.E) return fail(SNK_EINVAL, "obs target too small: %zu < %zu", bytes, (size_t)h->p.N * h->p.E);
-  h->p.obs = d_obs;
+  const size_t need = (size_t)h->p.N * h->obs_out_env_bytes;
+  if (bytes < need) return fail(SNK_EINVAL, "obs target too small: %zu < %zu", bytes, need);
+  h->d_obs_user = d_obs;
+  if (!atari) h->p.obs = d_obs;  // native mode: the step kernel writes straight into the target
   return SNK_OK;
 }
 
@@ -432,7 +459,8 @@ extern "C" int snk_algorithmic_bytes_per_step(const snk_config* c, double mean_s
   if (rc) return rc;
   if (!out) return fail(SNK_EINVAL, "out is NULL");
   const double V = c->size + 2.0, S = c->n_snakes, F = c->n_fruits, K = c->n_views ? c->n_views : c->n_snakes;
-  *out = K * V * V * 3.0 + 19.0 * S + 2.0 * mean_sum_len + 2.0 * F + 30.0;
+  const double side = c->obs_mode == SNK_OBS_ATARI84 ? 84.0 : V;
+  *out = K * side * side * 3.0 + 19.0 * S + 2.0 * mean_sum_len + 2.0 * F + 30.0;
   return SNK_OK;
 }
 

@@ -629,6 +629,58 @@ __global__ void __launch_bounds__(256) k_step_rows(const Params p) {
   if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
+
+// k_upscale84: obs_mode = SNK_OBS_ATARI84, the reference's WarpFrame (utils.py:27-31):
+// cv2.resize(frame, (84, 84), INTER_AREA), which for 84 % V == 0 is exact r x r pixel replication
+// (r = 84 / V).  One CTA per env: the native [V][V][3K] image is staged in shared memory, every
+// thread replicates source pixels into the 84x84 image (also in shared memory), and one TMA bulk
+// copy streams the 7056*3K bytes out (always a multiple of 16, so every env is an aligned unit).
+__global__ void __launch_bounds__(256) k_upscale84(const u8* __restrict__ native, u8* __restrict__ out, long long N, int V, int C) {
+  extern __shared__ __align__(128) u8 smem[];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int E = V * V * C, r = 84 / V, OUT = 84 * 84 * C;
+  u8* dst = smem;
+  u8* src = smem + ((OUT + 127) & ~127);
+  for (long long e = blockIdx.x; e < N; e += gridDim.x) {
+    const u8* g = native + e * (long long)E;
+    if ((E & 1) == 0) {
+      const u16* g16 = reinterpret_cast<const u16*>(g);
+      u16* s16 = reinterpret_cast<u16*>(src);
+      for (int i = tid; i < E / 2; i += nthr) s16[i] = g16[i];
+    } else {
+      for (int i = tid; i < E; i += nthr) src[i] = g[i];
+    }
+    if (tid == 0) bulk_wait_read();  // the previous image has left shared memory
+    __syncthreads();
+    for (int sp = tid; sp < V * V; sp += nthr) {
+      const int x = sp / V, y = sp - x * V;
+      const u8* spx = src + sp * C;
+      for (int dx = 0; dx < r; ++dx) {
+        u8* row = dst + ((x * r + dx) * 84 + y * r) * C;
+        if ((C & 1) == 0) {
+          for (int j = 0; j < C / 2; ++j) {
+            const u16 v = reinterpret_cast<const u16*>(spx)[j];
+            for (int dy = 0; dy < r; ++dy) reinterpret_cast<u16*>(row + dy * C)[j] = v;
+          }
+        } else {
+          for (int j = 0; j < C; ++j) {
+            const u8 v = spx[j];
+            for (int dy = 0; dy < r; ++dy) row[dy * C + j] = v;
+          }
+        }
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      u8* gd = out + e * (long long)OUT;
+      for (int off = 0; off < OUT; off += 16384) bulk_store_s2g(gd + off, dst + off, (u32)min(16384, OUT - off));
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+}
+
 // ------------------------------------------------------------------ state dump / load, action stream
 // canonical blob <-> private layout; one thread per (env, snake); not on the hot path
 __global__ void k_dump(const Params p, u8* blob, snk_state_layout lay) {
@@ -830,6 +882,24 @@ cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm, int S, int K) {
     case SNK_RULES_ADVERSARIAL: return plan_rules<SNK_RULES_ADVERSARIAL>(plan, n_sm, S, K);
     default: return plan_rules<SNK_RULES_CUT>(plan, n_sm, S, K);
   }
+}
+
+cudaError_t snk_launch_upscale84(const uint8_t* native, uint8_t* out, long long N, int V, int C, int n_sm, cudaStream_t stream) {
+  const size_t smem = (((size_t)84 * 84 * C + 127) & ~(size_t)127) + (size_t)V * V * C + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(k_upscale84, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (err) return err;
+    attr_set = true;
+  }
+  int occ = 0;
+  cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upscale84, 256, smem);
+  if (err) return err;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  long long grid = (long long)n_sm * occ;
+  if (grid > N) grid = N;
+  k_upscale84<<<(unsigned)grid, 256, smem, stream>>>(native, out, N, V, C);
+  return cudaGetLastError();
 }
 
 cudaError_t snk_launch_dump(const Params& p, u8* blob, const snk_state_layout& lay, cudaStream_t stream) {

@@ -21,6 +21,7 @@ struct LaunchPlan {
 cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm, int S, int K);
 bool snk_lane_supported(int S, int K);
 cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, cudaStream_t stream);
+cudaError_t snk_launch_upscale84(const uint8_t* native, uint8_t* out, long long N, int V, int C, int n_sm, cudaStream_t stream);
 cudaError_t snk_launch_dump(const Params& p, uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);
 cudaError_t snk_launch_load(const Params& p, const uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);
 cudaError_t snk_launch_gen_actions(int8_t* actions, long long N, int S, long long env_id_base, uint64_t step,

@@ -35,12 +35,12 @@ class SnakeGymEnv(object):
     spec = None
 
     def __init__(self, size=(10, 10), n_snakes=2, n_fruits=None, n_views=None, rules="classic", screen_res=300,
-                 seed=0, device=0, max_steps=2000):
+                 seed=0, device=0, max_steps=2000, obs_mode="native"):
         # the reference passes kwargs by RE-CALLING __init__ on a made env (utils.py:38): allowed here too
         if getattr(self, "_venv", None) is not None:
             self._venv.close()
         self._kw = dict(size=size, n_snakes=n_snakes, n_fruits=n_fruits, n_views=n_views, rules=rules,
-                        screen_res=screen_res, device=device, max_steps=max_steps)
+                        screen_res=screen_res, device=device, max_steps=max_steps, obs_mode=obs_mode)
         self._seed = seed
         self._venv = SnakeVecEnv(1, seed=seed, auto_reset=False, **self._kw)
         self.action_space = self._venv.action_space

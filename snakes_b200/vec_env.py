@@ -77,18 +77,25 @@ class SnakeVecEnv(object):
     `size`, `n_snakes`, `n_fruits`, `screen_res` (accepted, unused: no pyglet viewer), plus the
     batch / device ones: `num_envs`, `rules` ('classic' | 'adversarial' | 'cut'), `n_views`
     (K; the reference's SnakeEnv emits 3, snake_multiple_test.py:93-95), `seed`, `device`,
-    `env_id_base` (global id of env 0: shard offset under multi-GPU), `auto_reset`.
+    `env_id_base` (global id of env 0: shard offset under multi-GPU), `auto_reset`, `obs_mode`
+    ('native' [V,V,3K] or 'atari84' [84,84,3K]: the reference's WarpFrame, utils.py:15-31; exact
+    pixel replication, so it needs 84 % (size + 2) == 0, e.g. size 10 or 19).
     """
 
     def __init__(self, num_envs, size=(10, 10), n_snakes=2, n_fruits=None, n_views=None, rules="classic",
-                 seed=0, device=0, env_id_base=0, auto_reset=True, max_steps=2000, screen_res=300, host_io=False):
+                 seed=0, device=0, env_id_base=0, auto_reset=True, max_steps=2000, screen_res=300, host_io=False,
+                 obs_mode="native"):
         import time
         self._L = _lib.lib()
         if isinstance(device, torch.device):
             device = device.index or 0
         elif isinstance(device, str):
             device = torch.device(device).index or 0
+        if obs_mode not in ("native", "atari84"):
+            raise ValueError("obs_mode must be 'native' or 'atari84'")
+        self.obs_mode = obs_mode
         self.cfg = _lib.make_config(num_envs, size, n_snakes, n_fruits, n_views, rules, max_steps, auto_reset,
+                                    obs_mode=_lib.OBS_ATARI84 if obs_mode == "atari84" else _lib.OBS_NATIVE,
                                     device=device, env_id_base=env_id_base, seed=seed)
         self.device = torch.device("cuda", self.cfg.device)
         torch.cuda.init()
@@ -104,8 +111,8 @@ class SnakeVecEnv(object):
         self.screen_res = screen_res
         self.host_io = host_io
         self.action_space = Discrete(6 if self.cfg.rules == _lib.RULES["cut"] else 5)
-        self.observation_space = Box(0, 255, (self.V, self.V, 3 * self.K), np.uint8)
         self._bind_buffers()
+        self.observation_space = Box(0, 255, tuple(self.obs.shape[1:]), np.uint8)
         self._actions = torch.zeros((self.N, self.S), dtype=torch.int8, device=self.device)
         self._pending = False
         self._tstart = time.time()
@@ -146,7 +153,7 @@ class SnakeVecEnv(object):
             raise _lib.SnkError("seed() must be called before the first reset()")
         self.close()
         self.__init__(self.N, self.D, self.S, self.F, self.K, self.rules, seed, self.cfg.device, self.cfg.env_id_base,
-                      bool(self.cfg.auto_reset), self.cfg.max_steps, self.screen_res, self.host_io)
+                      bool(self.cfg.auto_reset), self.cfg.max_steps, self.screen_res, self.host_io, self.obs_mode)
         return [int(seed)]
 
     def reset(self, mask=None):

@@ -137,3 +137,35 @@ def test_create_rejects_bad_config(sb):
         sb.SnakeVecEnv(4, size=(10, 12))
     with pytest.raises(ValueError):
         sb.SnakeVecEnv(4, rules="nope")
+
+
+@pytest.mark.parametrize("D,S,K,rules", [(19, 2, 2, "classic"), (10, 3, 3, "cut"), (10, 2, 3, "adversarial"), (12, 1, 1, "classic")])
+def test_atari84_obs_mode(sb, D, S, K, rules):
+    """obs_mode='atari84' = the reference's WarpFrame (utils.py:27-31): exact r x r replication of the
+    native image (cv2 INTER_AREA for integer factors, see tests/test_warpframe.py)."""
+    import torch
+    N = 200
+    kw = dict(size=D, n_snakes=S, n_views=K, rules=rules, seed=4)
+    env = sb.SnakeVecEnv(N, obs_mode="atari84", **kw)
+    co = c_oracle.COracle(N, **kw)
+    r = 84 // (D + 2)
+    up = lambda o: np.repeat(np.repeat(o, r, axis=1), r, axis=2)
+    assert env.observation_space.shape == (84, 84, 3 * K)
+    obs = env.reset()
+    assert obs.shape == (N, 84, 84, 3 * K)
+    assert np.array_equal(obs.cpu().numpy(), up(co.reset()))
+    for t in range(40):
+        a = c_oracle.gen_actions(co.cfg, t, 8, env.action_space.n)
+        obs, rew, done, _ = env.step(a)
+        cobs, crew, cdone, _ = co.step(a)
+        assert np.array_equal(obs.cpu().numpy(), up(cobs)), t
+        assert np.array_equal(rew.cpu().numpy(), crew) and np.array_equal(done.cpu().numpy(), cdone)
+    # straight into a rollout slot
+    rollout = torch.zeros((2, N, 84, 84, 3 * K), dtype=torch.uint8, device=env.device)
+    env.set_obs_target(rollout[1])
+    a = c_oracle.gen_actions(co.cfg, 40, 8, env.action_space.n)
+    env.step(a)
+    assert np.array_equal(rollout[1].cpu().numpy(), up(co.step(a)[0]))
+    env.close()
+    with pytest.raises(sb.SnkError):
+        sb.SnakeVecEnv(4, size=9, obs_mode="atari84")
