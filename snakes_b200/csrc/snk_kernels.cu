@@ -204,7 +204,7 @@ __device__ __forceinline__ void store_image(const Params& p, const u8* tile, int
           bulk_store_s2g_hint(gdst + off, tile + off, (u32)min(16384, tile_bytes - off), pol);
       }
       bulk_commit();
-      bulk_wait_read();
+      if (!(p.debug & 16)) bulk_wait_read();
     }
   } else if (left >= p.TE) {
     const uint4* src = reinterpret_cast<const uint4*>(tile);
