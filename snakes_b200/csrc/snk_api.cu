@@ -198,7 +198,10 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   // their images (default: fastest measured), warp-specialised single kernel, or two kernels
   {
     const char* lv = getenv("SNK_LANE");
-    plan.ws = plan.kind == KIND_LANE && lv && !strcmp(lv, "ws");
+    // measured on B200: with a small image per env (3 views of 12x12: 1296 B) the step is bound by the
+    // logic's latency and the warp-specialised form (more logic warps per image buffer) is 1.4x faster;
+    // with 2646 B per env (2 views of 21x21) the image stream dominates and the fused form wins
+    plan.ws = plan.kind == KIND_LANE && (lv ? !strcmp(lv, "ws") : p.E < 2048);
     plan.split = plan.kind == KIND_LANE && lv && !strcmp(lv, "split");
     const char* lw = getenv("SNK_LOGIC_WARPS");
     p.PW = 2;

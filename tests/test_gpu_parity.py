@@ -88,6 +88,7 @@ CONFIGS = [
     ("classic", 1, 10, 1, 1, 1, 300),        # configs[0]: a single env
     ("classic", 1, 10, 1, 3, 33, 200),       # more views than snakes
     ("classic", 4, 7, 6, 2, 300, 300),       # F > S, K < S
+    ("classic", 2, 10, 4, 2, 500, 300),      # NewMultipleSnakes defaults: 2 snakes, 4 fruits
     ("classic", 3, 3, 3, 3, 256, 300),       # crowded board: no-free-cell + alias paths
     ("adversarial", 3, 10, 3, 3, 500, 400),
     ("adversarial", 2, 5, 2, 2, 129, 400),
@@ -291,7 +292,7 @@ def test_shard_invariance(sb):
         e.close()
 
 
-@pytest.mark.parametrize("variant", ["ws", "split"])
+@pytest.mark.parametrize("variant", ["fused", "ws", "split"])
 def test_lane_kernel_variants_match_oracle(sb, monkeypatch, variant):
     """The alternative forms of the lane path (warp-specialised single kernel; logic + paint as two
     kernels) produce the same bytes as the default fused form."""
