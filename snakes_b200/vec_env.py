@@ -259,6 +259,25 @@ class SnakeVecEnv(object):
     def dump_state(self):
         return split_state(self.dump_state_blob(), self.lay, self.cfg)
 
+    def save(self, path):
+        """Checkpoint of the env state (the reference never checkpoints it; its learner only saves
+        model parameters, ppo_multi_agent_new.py:104-106).  A .npz with the constructor arguments
+        and the canonical state blob; `SnakeVecEnv.load(path)` resumes bit-exactly."""
+        c = self.cfg
+        np.savez_compressed(path, blob=self.dump_state_blob(), num_envs=c.num_envs, size=c.size, n_snakes=c.n_snakes,
+                            n_fruits=c.n_fruits, n_views=c.n_views, rules=self.rules, max_steps=c.max_steps,
+                            auto_reset=c.auto_reset, env_id_base=c.env_id_base, seed=np.uint64(c.seed), obs_mode=self.obs_mode)
+
+    @classmethod
+    def load(cls, path, device=0, host_io=False):
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        env = cls(int(z["num_envs"]), int(z["size"]), int(z["n_snakes"]), int(z["n_fruits"]), int(z["n_views"]), str(z["rules"]),
+                  int(z["seed"]), device, int(z["env_id_base"]), bool(z["auto_reset"]), int(z["max_steps"]), host_io=host_io,
+                  obs_mode=str(z["obs_mode"]))
+        env.load_state_blob(z["blob"])
+        env.reset(mask=torch.zeros(env.N, dtype=torch.bool, device=env.device))  # re-encode the observations
+        return env
+
     def gen_actions(self, step, seed=1, out=None):
         """Synthetic uniform action stream (Philox key (seed, global env id)), generated on device."""
         out = self._actions if out is None else out

@@ -169,3 +169,27 @@ def test_atari84_obs_mode(sb, D, S, K, rules):
     env.close()
     with pytest.raises(sb.SnkError):
         sb.SnakeVecEnv(4, size=9, obs_mode="atari84")
+
+
+@pytest.mark.parametrize("rules,S,D", [("classic", 2, 19), ("adversarial", 3, 10), ("cut", 16, 64)])
+def test_checkpoint_resume_is_bit_exact(sb, tmp_path, rules, S, D):
+    """save() / load(): the resumed env continues exactly like the original (state incl. RNG counters)."""
+    N = 96 if D < 64 else 12
+    env = sb.SnakeVecEnv(N, size=D, n_snakes=S, rules=rules, seed=77, env_id_base=1000)
+    env.reset()
+    for t in range(30):
+        env.step(env.gen_actions(t, 6))
+    path = str(tmp_path / "ckpt.npz")
+    env.save(path)
+    twin = sb.SnakeVecEnv.load(path)
+    assert np.array_equal(twin.obs.cpu().numpy(), env.obs.cpu().numpy())
+    for t in range(30, 60):
+        a = env.gen_actions(t, 6).clone()
+        o1, r1, d1, _ = env.step(a)
+        o2, r2, d2, _ = twin.step(a.cpu().numpy())
+        assert np.array_equal(o1.cpu().numpy(), o2.cpu().numpy()), t
+        assert np.array_equal(r1.cpu().numpy(), r2.cpu().numpy()) and np.array_equal(d1.cpu().numpy(), d2.cpu().numpy())
+    s1, s2 = env.dump_state(), twin.dump_state()
+    for k in s1:
+        assert np.array_equal(s1[k], s2[k]), k
+    env.close(); twin.close()
