@@ -89,3 +89,48 @@ def lists_from_state(st, cfg, e=0):
         fruits = sorted(xy(p) for p in np.flatnonzero(st["fruit_grid"][e]) for _ in range(int(st["fruit_grid"][e][p])))
     return {"snakes": snakes, "fruits": fruits, "vels": [vel_xy[int(v)] for v in st["vel"][e]],
             "grow_to": [int(x) for x in st["grow_to"][e]], "t": int(st["t"][e]), "spare": int(st["spare"][e])}
+
+
+def random_long_snake_states(lay, cfg, rng, min_len=20, max_len=70):
+    """A canonical state blob with long, self-avoiding, mutually disjoint bodies (random walks):
+    exercises multi-word chain codes, ring wrap-around and crowded boards from step 0."""
+    N, S, F, D = cfg.num_envs, cfg.n_snakes, cfg.n_fruits, cfg.size
+    V = D + 2
+    blob = np.zeros(lay.total_bytes, dtype=np.uint8)
+    st = c_oracle.split_state(blob, lay, cfg)
+    moves = {1: (1, 0), 2: (0, 1), 3: (-1, 0), 4: (0, -1)}
+    pid = lambda x, y: (x + 1) * V + (y + 1)
+    for e in range(N):
+        used = set()
+        for s in range(S):
+            for _attempt in range(50):
+                x, y = int(rng.randint(D)), int(rng.randint(D))
+                if (x, y) not in used:
+                    break
+            walk, vel = [(x, y)], 0
+            seen = {(x, y)}
+            target = int(rng.randint(min_len, max_len + 1))
+            while len(walk) < target:
+                opts = [(a, (walk[-1][0] + dx, walk[-1][1] + dy)) for a, (dx, dy) in moves.items()]
+                opts = [(a, c) for a, c in opts if 0 <= c[0] < D and 0 <= c[1] < D and c not in seen and c not in used]
+                if not opts:
+                    break
+                a, c = opts[int(rng.randint(len(opts)))]
+                walk.append(c); seen.add(c); vel = a
+            used |= seen
+            body = walk[::-1]  # head = last cell reached
+            L = len(body)
+            st["len"][e, s] = L
+            st["body"][e, s, :L] = [pid(cx, cy) for cx, cy in body]
+            st["grow_to"][e, s] = max(3, L + int(rng.randint(0, 3)))
+            st["vel"][e, s] = vel
+        st["t"][e] = int(rng.randint(0, 100))
+        st["ep_len"][e] = st["t"][e]
+        free = [(x, y) for x in range(D) for y in range(D) if (x, y) not in used]
+        for f in range(F):
+            fx, fy = free[int(rng.randint(len(free)))] if free else (0, 0)
+            if lay.fruit_is_grid:
+                st["fruit_grid"][e, pid(fx, fy)] += 1
+            else:
+                st["fruit"][e, f] = pid(fx, fy)
+    return blob

@@ -307,3 +307,36 @@ def test_lane_kernel_variants_match_oracle(sb, monkeypatch, variant):
             _compare_step(env, co, a, "%s %s step %d" % (variant, rules, t), check_state=(t % 10 == 0))
         env.close()
     monkeypatch.delenv("SNK_LANE")
+
+
+@pytest.mark.parametrize("rules,S,D,kernel", [("classic", 2, 19, None), ("cut", 3, 19, None), ("adversarial", 2, 14, None),
+                                               ("classic", 2, 19, "tile"), ("cut", 3, 14, "dense"), ("classic", 4, 30, "rows")])
+def test_injected_long_snakes(sb, monkeypatch, rules, S, D, kernel):
+    """Random long bodies (20-70 segments) loaded through snk_load_state into device and oracle, then
+    stepped with actions biased to keep moving: multi-word chain codes, carries, cuts of long bodies."""
+    if kernel:
+        monkeypatch.setenv("SNK_FORCE_KERNEL", kernel)
+    N = 96
+    kw = dict(size=D, n_snakes=S, rules=rules, seed=31, n_views=4 if kernel == "rows" else None)
+    env = sb.SnakeVecEnv(N, **kw)
+    co = c_oracle.COracle(N, **kw)
+    rng = np.random.RandomState(8)
+    blob = helpers.random_long_snake_states(co.lay, co.cfg, rng)
+    co.load_state(blob)
+    env.load_state_blob(blob)
+    env.check_errors()
+    _state_equal(env.dump_state(), co.state(), "after load")
+    import torch
+    env.reset(mask=torch.zeros(N, dtype=torch.bool, device=env.device))
+    assert np.array_equal(env.obs.cpu().numpy(), co.observe())
+    nact = env.action_space.n
+    longest = 0
+    for t in range(120):
+        a = rng.randint(0, nact, size=(N, S)).astype(np.int8)
+        a[rng.rand(N, S) < 0.6] = 0  # mostly keep going straight so that long bodies survive a while
+        _compare_step(env, co, a, "long %s %s step %d" % (rules, kernel, t), check_state=(t % 5 == 0))
+        longest = max(longest, int(co.state()["len"].max()))
+    assert longest >= 40
+    env.close()
+    if kernel:
+        monkeypatch.delenv("SNK_FORCE_KERNEL")
