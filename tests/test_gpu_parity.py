@@ -340,3 +340,24 @@ def test_injected_long_snakes(sb, monkeypatch, rules, S, D, kernel):
     env.close()
     if kernel:
         monkeypatch.delenv("SNK_FORCE_KERNEL")
+
+
+def test_cut_equals_classic_without_strikes_full_size(sb):
+    """Size-independent property at BASELINE configs[2] size (65536 envs, 3 snakes, 10x10): with actions
+    in {0..4} the cut rule-set produces exactly the classic observations, rewards and dones."""
+    import torch
+    N = 65536
+    kw = dict(size=10, n_snakes=3, seed=2)
+    a_env = sb.SnakeVecEnv(N, rules="classic", **kw)
+    b_env = sb.SnakeVecEnv(N, rules="cut", **kw)
+    assert torch.equal(a_env.reset(), b_env.reset())
+    acts = torch.empty((N, 3), dtype=torch.int8, device=a_env.device)
+    for t in range(60):
+        a_env.gen_actions(t, 9, out=acts)  # classic action space: values 0..4
+        oa, ra, da, _ = a_env.step(acts)
+        ob, rb, db, _ = b_env.step(acts)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), t
+    sa, sb_ = a_env.dump_state(), b_env.dump_state()
+    for k in ("t", "len", "grow_to", "vel", "body", "draw_ctr"):
+        assert np.array_equal(sa[k], sb_[k]), k
+    a_env.close(); b_env.close()
