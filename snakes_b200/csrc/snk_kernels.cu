@@ -635,10 +635,53 @@ __global__ void __launch_bounds__(256) k_step_rows(const Params p) {
 // (r = 84 / V).  One CTA per env: the native [V][V][3K] image is staged in shared memory, every
 // thread replicates source pixels into the 84x84 image (also in shared memory), and one TMA bulk
 // copy streams the 7056*3K bytes out (always a multiple of 16, so every env is an aligned unit).
-__global__ void __launch_bounds__(256) k_upscale84(const u8* __restrict__ native, u8* __restrict__ out, long long N, int V, int C) {
+// one source pixel -> R rows of R copies; compile-time pixel size C and factor R (0 = runtime)
+template <int CT, int RT>
+__device__ __forceinline__ void upscale_pixel(const u8* spx, u8* dst0, int C, int r) {
+  if constexpr (CT > 0 && (CT % 2) == 0 && ((RT * CT) % 8) == 0) {
+    // the R*C-byte run is a periodic pattern of C/2 halfwords: build it once as 64-bit words
+    constexpr int NH = CT / 2, NQ = RT * CT / 8;
+    u64 h[NH];
+#pragma unroll
+    for (int j = 0; j < NH; ++j) h[j] = reinterpret_cast<const u16*>(spx)[j];
+    u64 q[NQ];
+#pragma unroll
+    for (int w = 0; w < NQ; ++w) q[w] = h[(4 * w) % NH] | h[(4 * w + 1) % NH] << 16 | h[(4 * w + 2) % NH] << 32 | h[(4 * w + 3) % NH] << 48;
+#pragma unroll
+    for (int dx = 0; dx < RT; ++dx) {
+      u64* row = reinterpret_cast<u64*>(dst0 + dx * 84 * CT);
+#pragma unroll
+      for (int w = 0; w < NQ; ++w) row[w] = q[w];
+    }
+  } else if constexpr (CT > 0) {
+    u8 v[CT];
+#pragma unroll
+    for (int j = 0; j < CT; ++j) v[j] = spx[j];
+#pragma unroll
+    for (int dx = 0; dx < RT; ++dx) {
+      u8* row = dst0 + dx * 84 * CT;
+#pragma unroll
+      for (int dy = 0; dy < RT; ++dy)
+#pragma unroll
+        for (int j = 0; j < CT; ++j) row[dy * CT + j] = v[j];
+    }
+  } else {
+    for (int dx = 0; dx < r; ++dx) {
+      u8* row = dst0 + dx * 84 * C;
+      for (int j = 0; j < C; ++j) {
+        const u8 v = spx[j];
+        for (int dy = 0; dy < r; ++dy) row[dy * C + j] = v;
+      }
+    }
+  }
+}
+
+template <int CT, int RT>
+__global__ void __launch_bounds__(256) k_upscale84(const u8* __restrict__ native, u8* __restrict__ out, long long N, int V, int C_) {
   extern __shared__ __align__(128) u8 smem[];
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int E = V * V * C, r = 84 / V, OUT = 84 * 84 * C;
+  const int C = CT > 0 ? CT : C_, r = RT > 0 ? RT : 84 / V;
+  const int E = V * V * C, OUT = 84 * 84 * C;
   u8* dst = smem;
   u8* src = smem + ((OUT + 127) & ~127);
   for (long long e = blockIdx.x; e < N; e += gridDim.x) {
@@ -654,21 +697,7 @@ __global__ void __launch_bounds__(256) k_upscale84(const u8* __restrict__ native
     __syncthreads();
     for (int sp = tid; sp < V * V; sp += nthr) {
       const int x = sp / V, y = sp - x * V;
-      const u8* spx = src + sp * C;
-      for (int dx = 0; dx < r; ++dx) {
-        u8* row = dst + ((x * r + dx) * 84 + y * r) * C;
-        if ((C & 1) == 0) {
-          for (int j = 0; j < C / 2; ++j) {
-            const u16 v = reinterpret_cast<const u16*>(spx)[j];
-            for (int dy = 0; dy < r; ++dy) reinterpret_cast<u16*>(row + dy * C)[j] = v;
-          }
-        } else {
-          for (int j = 0; j < C; ++j) {
-            const u8 v = spx[j];
-            for (int dy = 0; dy < r; ++dy) row[dy * C + j] = v;
-          }
-        }
-      }
+      upscale_pixel<CT, RT>(src + sp * C, dst + ((x * r) * 84 + y * r) * C, C, r);
     }
     fence_async_smem();
     __syncthreads();
@@ -679,6 +708,20 @@ __global__ void __launch_bounds__(256) k_upscale84(const u8* __restrict__ native
     }
   }
   if (tid == 0) bulk_wait_all();
+}
+
+template <int CT, int RT>
+static cudaError_t launch_upscale(const uint8_t* native, uint8_t* out, long long N, int V, int C, int n_sm, cudaStream_t stream) {
+  const size_t smem = (((size_t)84 * 84 * C + 127) & ~(size_t)127) + (size_t)V * V * C + 16;
+  cudaError_t err = cudaFuncSetAttribute(k_upscale84<CT, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err) return err;
+  int occ = 0;
+  if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upscale84<CT, RT>, 256, smem))) return err;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  long long grid = (long long)n_sm * occ;
+  if (grid > N) grid = N;
+  k_upscale84<CT, RT><<<(unsigned)grid, 256, smem, stream>>>(native, out, N, V, C);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ state dump / load, action stream
@@ -885,21 +928,15 @@ cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm, int S, int K) {
 }
 
 cudaError_t snk_launch_upscale84(const uint8_t* native, uint8_t* out, long long N, int V, int C, int n_sm, cudaStream_t stream) {
-  const size_t smem = (((size_t)84 * 84 * C + 127) & ~(size_t)127) + (size_t)V * V * C + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t err = cudaFuncSetAttribute(k_upscale84, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (err) return err;
-    attr_set = true;
-  }
-  int occ = 0;
-  cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upscale84, 256, smem);
-  if (err) return err;
-  if (occ < 1) return cudaErrorInvalidConfiguration;
-  long long grid = (long long)n_sm * occ;
-  if (grid > N) grid = N;
-  k_upscale84<<<(unsigned)grid, 256, smem, stream>>>(native, out, N, V, C);
-  return cudaGetLastError();
+  const int r = 84 / V;
+  if (C == 6 && r == 4) return launch_upscale<6, 4>(native, out, N, V, C, n_sm, stream);   // 2 views of 21x21 (the headline board)
+  if (C == 12 && r == 4) return launch_upscale<12, 4>(native, out, N, V, C, n_sm, stream);  // 4 views of 21x21
+  if (C == 6 && r == 7) return launch_upscale<6, 7>(native, out, N, V, C, n_sm, stream);    // 2 views of 12x12
+  if (C == 9 && r == 7) return launch_upscale<9, 7>(native, out, N, V, C, n_sm, stream);    // 3 views of 12x12 (SnakeEnv's K = 3)
+  if (C == 9 && r == 4) return launch_upscale<9, 4>(native, out, N, V, C, n_sm, stream);    // 3 views of 21x21
+  if (C == 3 && r == 7) return launch_upscale<3, 7>(native, out, N, V, C, n_sm, stream);
+  if (C == 3 && r == 4) return launch_upscale<3, 4>(native, out, N, V, C, n_sm, stream);
+  return launch_upscale<0, 0>(native, out, N, V, C, n_sm, stream);
 }
 
 cudaError_t snk_launch_dump(const Params& p, u8* blob, const snk_state_layout& lay, cudaStream_t stream) {
