@@ -488,7 +488,11 @@ __global__ void __launch_bounds__(256) k_step_dense(const Params p) {
       if (tid < F) code[fr[tid]] = 1;
     } else {
       const u8* grid = p.grid + e * p.grid_stride;
-      for (int i = tid; i < VV; i += nthr) if (grid[i]) code[i] = 1;
+      const u32* g32 = reinterpret_cast<const u32*>(grid);  // grid_stride is a multiple of 16
+      for (int w = tid; w < (VV + 3) / 4; w += nthr) {
+        u32 word = g32[w];
+        for (int q = 0; word; ++q, word >>= 8) if ((word & 0xff) && 4 * w + q < VV) code[4 * w + q] = 1;
+      }
     }
     __syncthreads();
     const u16* rings = p.body + e * S * cap;
@@ -560,7 +564,11 @@ __global__ void __launch_bounds__(256) k_step_rows(const Params p) {
       if (tid < F) code[fr[tid]] = 1;
     } else {
       const u8* grid = p.grid + e * p.grid_stride;
-      for (int i = tid; i < VV; i += nthr) if (grid[i]) code[i] = 1;
+      const u32* g32 = reinterpret_cast<const u32*>(grid);  // grid_stride is a multiple of 16
+      for (int w = tid; w < (VV + 3) / 4; w += nthr) {
+        u32 word = g32[w];
+        for (int q = 0; word; ++q, word >>= 8) if ((word & 0xff) && 4 * w + q < VV) code[4 * w + q] = 1;
+      }
     }
     __syncthreads();
     const u16* rings = p.body + e * S * cap;
