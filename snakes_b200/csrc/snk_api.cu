@@ -220,9 +220,9 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     p.W = W; plan.block = 32 * W; plan.smem = smem_tile;
     p.n_groups = (N + W - 1) / W;
   } else if (plan.kind == KIND_ROWS) {
-    p.W = 1; p.R = R; { const char* rb = getenv("SNK_ROWS_BLOCK"); plan.block = rb ? atoi(rb) : (cfg->rules == SNK_RULES_CLASSIC ? 128 : 64); }
+    p.W = 1; p.R = R; { const char* rb = getenv("SNK_ROWS_BLOCK"); plan.block = rb ? atoi(rb) : 160; }  // 1 producer warp + 4 consumer warps
     p.tile_stride = (int)(((size_t)R * V * p.C + 127) & ~(size_t)127);
-    plan.smem = (((size_t)p.VV + 127) & ~(size_t)127) + 2 * (size_t)p.tile_stride + (size_t)(p.RW + p.bm_words) * 4;
+    plan.smem = 2 * (((size_t)p.VV + 127) & ~(size_t)127) + 2 * (size_t)p.tile_stride + (size_t)(p.RW + p.bm_words) * 4;
     p.n_groups = N;
   } else {
     p.W = 1; plan.block = 256; plan.smem = align16((size_t)p.VV) + (size_t)(p.RW + p.bm_words) * 4;

@@ -536,14 +536,17 @@ __device__ __forceinline__ void pattern3(u32 rgb, u32& w0, u32& w1, u32& w2) {  
   w0 = r | g << 8 | b << 16 | r << 24; w1 = g | b << 8 | r << 16 | g << 24; w2 = b | r << 8 | g << 16 | b << 24;
 }
 
+__device__ __forceinline__ void consumer_sync(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
+
 template <int RULES>
-__global__ void __launch_bounds__(256) k_step_rows(const Params p) {
+__global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
   extern __shared__ __align__(128) u8 smem[];
   __shared__ double s_stats[SNK_NSTATS];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = p.S, F = p.F, K = p.K, C = p.C, VV = p.VV, V = p.V, cap = p.cap, R = p.R;
-  u8* code = smem;  // [VV] 0 empty, 1 fruit, 3+2s body of s, 4+2s head of s, 255 border
-  u8* tiles = smem + ((VV + 127) & ~127);
+  const int code_stride = (VV + 127) & ~127;
+  u8* codes = smem;  // two grids [VV]: 0 empty, 1 fruit, 3+2s body of s, 4+2s head of s, 255 border
+  u8* tiles = smem + 2 * code_stride;
   u32* sc = reinterpret_cast<u32*>(tiles + 2 * p.tile_stride);
   u32* bm = sc + p.RW;
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
@@ -551,92 +554,107 @@ __global__ void __launch_bounds__(256) k_step_rows(const Params p) {
   WarpStats st = {0, 0, 0, 0, 0, 0, 0, 0};
   u32 errs = 0;
   const int n_chunks = (V + R - 1) / R;
-  int issued = 0;  // chunks handed to the TMA engine so far (thread 0's bulk groups)
-  for (long long e = blockIdx.x; e < p.N; e += gridDim.x) {
-    if (warp == 0) advance_env<RULES>(p, e, lane, sc, bm, errs, st);
-    for (int i = tid; i < VV; i += nthr) code[i] = 0;
-    __syncthreads();
-    // Codes grow in paint order (fruit 1 < snake s body 3+2s < head 4+2s < border 255), so "a later
-    // item overwrites an earlier one" is a per-cell MAX.  All snakes are painted at once; a pass is
-    // repeated until no thread had to raise a cell (cells shared by two snakes are rare).
-    if (RULES == SNK_RULES_CLASSIC) {
-      const u16* fr = reinterpret_cast<const u16*>(sc + REC_SNAKE0 + 2 * S);
-      if (tid < F) code[fr[tid]] = 1;
-    } else {
-      const u8* grid = p.grid + e * p.grid_stride;
-      const u32* g32 = reinterpret_cast<const u32*>(grid);  // grid_stride is a multiple of 16
-      for (int w = tid; w < (VV + 3) / 4; w += nthr) {
-        u32 word = g32[w];
-        for (int q = 0; word; ++q, word >>= 8) if ((word & 0xff) && 4 * w + q < VV) code[4 * w + q] = 1;
-      }
-    }
-    __syncthreads();
-    const u16* rings = p.body + e * S * cap;
-    for (int pass = 0; pass < 64; ++pass) {
-      int changed = 0;
-      for (int s = 0; s < S; ++s) {
-        const u32 a = sc[REC_SNAKE0 + 2 * s];
-        const int len = a >> 16, hs = a & 0xffff;
-        for (int i = tid; i < len; i += nthr) {
-          const int cell = ring_at(rings + s * cap, hs, i, cap);
-          const u8 mine = (u8)(3 + 2 * s + (i == 0));
-          if (code[cell] < mine) { code[cell] = mine; changed = 1; }
-        }
-      }
-      if (!__syncthreads_or(changed)) break;
-    }
-    for (int i = tid; i < V; i += nthr) { code[i] = 255; code[(V - 1) * V + i] = 255; code[i * V] = 255; code[i * V + V - 1] = 255; }
-    __syncthreads();
-    u8* out = p.obs + e * (long long)p.E;
-    for (int c = 0; c < n_chunks; ++c) {
-      u8* tile = tiles + (issued & 1) * p.tile_stride;
-      if (issued >= 2) {  // the copy that last used this buffer has been read by the engine
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncthreads();
-      }
-      const int r0 = c * R, rows = min(R, V - r0), cells = rows * V;
-      for (int i = tid; i < cells; i += nthr) {
-        const int cd = code[r0 * V + i];
-        u32 rgb = 0;
-        int self = -1;
-        if (cd == 1) rgb = 255u;
-        else if (cd == 255) rgb = 0xffffffu;
-        else if (cd >= 3) { self = (cd - 3) >> 1; rgb = snake_rgb(false, (cd - 3) & 1); }
-        u32 w0, w1, w2;
-        pattern3(rgb, w0, w1, w2);
-        u8* px = tile + i * C;
-        if ((C & 15) == 0) {
-          uint4* q = reinterpret_cast<uint4*>(px);
-          for (int j = 0; j < C / 16; ++j) {  // word index 4j: period 3 words
-            const int ph = (4 * j) % 3;
-            const u32 a0 = ph == 0 ? w0 : ph == 1 ? w1 : w2, a1 = ph == 0 ? w1 : ph == 1 ? w2 : w0, a2 = ph == 0 ? w2 : ph == 1 ? w0 : w1;
-            q[j] = make_uint4(a0, a1, a2, a0);
+  int issued = 0;  // chunks handed to the TMA engine so far (bulk groups of the consumers' thread 0)
+  // Software pipeline over envs: warp 0 (producer) steps env e_next and builds its code grid while
+  // warps 1..4 (consumers) expand and stream out the image of env e from the other grid.
+  long long e = blockIdx.x;
+  for (int it = 0;; ++it, e += gridDim.x) {
+    if (warp == 0) {
+      // iteration `it` consumes grid it & 1 (env e) and builds grid (it + 1) & 1 (env e + gridDim.x);
+      // iteration 0 first builds grid 0 as well
+      const long long eb = it == 0 ? e : e + gridDim.x;
+      for (int rep = 0; rep < (it == 0 ? 2 : 1); ++rep) {
+        const long long en = rep == 0 ? eb : eb + gridDim.x;
+        u8* code = codes + ((it == 0 ? rep : it + 1) & 1) * code_stride;
+        if (en >= p.N) continue;
+        advance_env<RULES>(p, en, lane, sc, bm, errs, st);
+        uint4* c16 = reinterpret_cast<uint4*>(code);
+        for (int i = lane; i < code_stride / 16; i += 32) c16[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        if (RULES == SNK_RULES_CLASSIC) {
+          const u16* fr = reinterpret_cast<const u16*>(sc + REC_SNAKE0 + 2 * S);
+          if (lane < F) code[fr[lane]] = 1;
+        }  // count-grid rules: the consumers read the fruit grid themselves (it is stable while env `en` is output)
+        __syncwarp();
+        // codes grow in paint order, so "later overwrites earlier" is a per-cell max: all snakes at
+        // once, repeated until no lane had to raise a cell (cells shared by two snakes are rare)
+        const u16* rings = p.body + en * S * cap;
+        for (int pass = 0; pass < 64; ++pass) {
+          int changed = 0;
+          for (int s = 0; s < S; ++s) {
+            const u32 a = sc[REC_SNAKE0 + 2 * s];
+            const int len = a >> 16, hs = a & 0xffff;
+            for (int i = lane; i < len; i += 32) {
+              const int cell = ring_at(rings + s * cap, hs, i, cap);
+              const u8 mine = (u8)(3 + 2 * s + (i == 0));
+              if (code[cell] < mine) { code[cell] = mine; changed = 1; }
+            }
           }
-        } else {
-          for (int j = 0; j < C; ++j) px[j] = (u8)(rgb >> (8 * (j % 3)));
+          __syncwarp();
+          if (!__any_sync(FULL, changed)) break;
         }
-        if (self >= 0 && self < K) {
-          const u32 own = snake_rgb(true, (cd - 3) & 1);
-          px[3 * self] = (u8)own; px[3 * self + 1] = (u8)(own >> 8); px[3 * self + 2] = (u8)(own >> 16);
-        }
+        for (int i = lane; i < V; i += 32) { code[i] = 255; code[(V - 1) * V + i] = 255; code[i * V] = 255; code[i * V + V - 1] = 255; }
+        __syncwarp();
       }
-      fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        const int bytes = cells * C;
-        for (int off = 0; off < bytes; off += 16384)
-          bulk_store_s2g(out + (long long)r0 * V * C + off, tile + off, (u32)min(16384, bytes - off));
-        bulk_commit();
-      }
-      ++issued;
     }
+    if (it == 0) __syncthreads();  // grid 0 ready
+    if (e >= p.N) break;
+    if (warp > 0) {
+      const int ct = tid - 32, cn = blockDim.x - 32;
+      const u8* code = codes + (it & 1) * code_stride;
+      const u8* fgrid = RULES == SNK_RULES_CLASSIC ? nullptr : p.grid + e * p.grid_stride;
+      u8* out = p.obs + e * (long long)p.E;
+      for (int c = 0; c < n_chunks; ++c) {
+        u8* tile = tiles + (issued & 1) * p.tile_stride;
+        if (issued >= 2) {  // the copy that last used this buffer has been read by the engine
+          if (ct == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          consumer_sync(cn);
+        }
+        const int r0 = c * R, rows = min(R, V - r0), cells = rows * V;
+        for (int i = ct; i < cells; i += cn) {
+          int cd = code[r0 * V + i];
+          if (RULES != SNK_RULES_CLASSIC && cd == 0 && fgrid[r0 * V + i]) cd = 1;  // fruit: lowest paint priority
+          u32 rgb = 0;
+          int self = -1;
+          if (cd == 1) rgb = 255u;
+          else if (cd == 255) rgb = 0xffffffu;
+          else if (cd >= 3) { self = (cd - 3) >> 1; rgb = snake_rgb(false, (cd - 3) & 1); }
+          u32 w0, w1, w2;
+          pattern3(rgb, w0, w1, w2);
+          u8* px = tile + i * C;
+          if ((C & 15) == 0) {
+            uint4* q = reinterpret_cast<uint4*>(px);
+            for (int j = 0; j < C / 16; ++j) {  // word index 4j: period 3 words
+              const int ph = (4 * j) % 3;
+              const u32 a0 = ph == 0 ? w0 : ph == 1 ? w1 : w2, a1 = ph == 0 ? w1 : ph == 1 ? w2 : w0, a2 = ph == 0 ? w2 : ph == 1 ? w0 : w1;
+              q[j] = make_uint4(a0, a1, a2, a0);
+            }
+          } else {
+            for (int j = 0; j < C; ++j) px[j] = (u8)(rgb >> (8 * (j % 3)));
+          }
+          if (self >= 0 && self < K) {
+            const u32 own = snake_rgb(true, (cd - 3) & 1);
+            px[3 * self] = (u8)own; px[3 * self + 1] = (u8)(own >> 8); px[3 * self + 2] = (u8)(own >> 16);
+          }
+        }
+        fence_async_smem();
+        consumer_sync(cn);
+        if (ct == 0) {
+          const int bytes = cells * C;
+          for (int off = 0; off < bytes; off += 16384)
+            bulk_store_s2g(out + (long long)r0 * V * C + off, tile + off, (u32)min(16384, bytes - off));
+          bulk_commit();
+        }
+        ++issued;
+      }
+    }
+    __syncthreads();  // grid (it + 1) & 1 built, grid it & 1 consumed
   }
-  if (tid == 0) bulk_wait_all();
+  if (tid == 32) bulk_wait_all();
   if (warp == 0) flush_stats(p, st, errs, s_stats, lane);
   __syncthreads();
   if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
-
 
 // k_upscale84: obs_mode = SNK_OBS_ATARI84, the reference's WarpFrame (utils.py:27-31):
 // cv2.resize(frame, (84, 84), INTER_AREA), which for 84 % V == 0 is exact r x r pixel replication
