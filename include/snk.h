@@ -157,6 +157,15 @@ int snk_step_host(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, float*
  * NULL restores the internal buffer.  Must be 16-byte aligned. */
 int snk_set_obs_target(snk_handle* h, uint8_t* d_obs, size_t bytes);
 
+/* T steps back to back into a caller-owned rollout buffer, no host round trip: step t reads
+ * d_actions[t] (int8 [T][N][S]) and writes its observations into d_obs[t] ([T][N][H][W][3K]), its
+ * rewards into d_reward[t] (float [T][N]) and its dones into d_done[t] (uint8 [T][N]).  Replaces the
+ * rollout loop of Runner.run (ppo_multi_agent_new.py:178-198: mb_obs / mb_rewards / mb_dones appends)
+ * for a scripted or pre-sampled action stream.  d_reward / d_done may be NULL.  Afterwards the
+ * handle's own buffers (snk_get_buffers) hold the last step, as after T calls of snk_step. */
+int snk_rollout(snk_handle* h, const int8_t* d_actions, int32_t T, uint8_t* d_obs, float* d_reward,
+                uint8_t* d_done, void* stream);
+
 /* Replay mode: per-env tapes of the reference's np_random.randint draws
  * (snake_multiple_test.py:200, :215).  CSR: env i owns vals/bounds[offsets[i] .. offsets[i+1]).
  * Host arrays, copied to the device (synchronous).  Switches the handle to SNK_RNG_TAPE. */

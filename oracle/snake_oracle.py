@@ -329,6 +329,28 @@ class SnakeOracle(object):
         ob[:, :, V - 1] = COL_WALL
         return np.ascontiguousarray(ob.transpose(1, 2, 0, 3)).reshape(V, V, 3 * K)
 
+    # -- get_ob_world (snake_multiple_test.py:60-91): one [V, V, 3] image, a colour pair per snake index
+    WORLD_COLOURS = (((0, 204, 0), (191, 242, 191)), ((0, 51, 204), (128, 154, 230)),
+                     ((204, 0, 119), (230, 128, 188)), ((119, 0, 204), (188, 128, 230)))
+
+    def world_view(self):
+        V = self.V
+        ob = np.zeros((V * V, 3), dtype=np.uint8)
+        if self.use_grid:
+            ob[np.flatnonzero(self.fruit_grid > 0)] = COL_FRUIT
+        else:
+            for f in self.fruit:
+                ob[f] = COL_FRUIT
+        for s, b in enumerate(self.body):
+            if b:
+                body_c, head_c = self.WORLD_COLOURS[s]  # the reference has 4 colour pairs (KeyError beyond)
+                ob[b] = body_c
+                ob[b[0]] = head_c
+        ob = ob.reshape(V, V, 3)
+        ob[0, :] = ob[V - 1, :] = COL_WALL
+        ob[:, 0] = ob[:, V - 1] = COL_WALL
+        return ob
+
     # -- canonical arrays (same layout as snk_dump_state, include/snk.h)
     def canonical(self, cap):
         S = self.S

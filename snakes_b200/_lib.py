@@ -48,6 +48,7 @@ _SIGNATURES = {
     "snk_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snk_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_set_obs_target": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "snk_set_draw_tape": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_state_layout_of": (C.c_int, [C.POINTER(SnkConfig), C.POINTER(SnkStateLayout)]),

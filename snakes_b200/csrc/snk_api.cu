@@ -187,7 +187,6 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   if (force && !strcmp(force, "lane") && !TE) { snk_destroy(h); return fail(SNK_EINVAL, "lane kernel does not support this configuration"); }
   p.family = plan.kind == KIND_LANE;
   { const char* sm = getenv("SNK_STORE"); p.store_mode = (sm && !strcmp(sm, "stg")) ? 1 : 0; }
-  { const char* dbg = getenv("SNK_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   {  // L2 policies (SNK_L2 = bit0 obs evict-first, bit1 records evict-last; testing aid)
     const char* l2 = getenv("SNK_L2");
     const int bits = l2 ? atoi(l2) : 3;
@@ -315,16 +314,30 @@ extern "C" int snk_get_buffers(const snk_handle* h, snk_buffers* out) {
   return SNK_OK;
 }
 
-static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_t* d_mask, cudaStream_t stream) {
+struct RolloutSlot {  // per-step output redirection of snk_rollout
+  uint8_t* obs;
+  float* reward;
+  uint8_t* done;
+};
+
+static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_t* d_mask, cudaStream_t stream,
+                  const RolloutSlot* slot = nullptr) {
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   Params p = h->p;
+  uint8_t* obs_user = h->d_obs_user;
+  if (slot) {
+    if (slot->reward) p.reward = slot->reward;
+    if (slot->done) p.done = slot->done;
+    obs_user = slot->obs;
+    if (h->cfg.obs_mode != SNK_OBS_ATARI84) p.obs = slot->obs;
+  }
   p.mode = mode; p.actions = d_actions; p.mask = d_mask;
   p.tape_vals = h->d_tape_vals; p.tape_bounds = h->d_tape_bounds; p.tape_off = h->d_tape_off;
   if (p.rng_mode == SNK_RNG_TAPE && !p.tape_vals) return fail(SNK_EINVAL, "rng_mode is TAPE but no tape was set");
   CUDA_TRY(snk_launch_step(p, h->cfg.rules, h->plan, stream));
   h->launches += (h->plan.split && mode != MODE_OBSERVE) ? 2 : 1;
   if (h->cfg.obs_mode == SNK_OBS_ATARI84) {
-    CUDA_TRY(snk_launch_upscale84(p.obs, h->d_obs_user, p.N, p.V, p.C, h->n_sm, stream));
+    CUDA_TRY(snk_launch_upscale84(p.obs, obs_user, p.N, p.V, p.C, h->n_sm, stream));
     h->launches++;
   }
   return SNK_OK;
@@ -338,6 +351,31 @@ extern "C" int snk_reset(snk_handle* h, const uint8_t* d_mask, void* stream) {
 extern "C" int snk_step(snk_handle* h, const int8_t* d_actions, void* stream) {
   if (!h || !d_actions) return fail(SNK_EINVAL, "NULL argument");
   return launch(h, MODE_STEP, d_actions, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int snk_rollout(snk_handle* h, const int8_t* d_actions, int32_t T, uint8_t* d_obs, float* d_reward, uint8_t* d_done,
+                           void* stream) {
+  if (!h || !d_actions || !d_obs || T < 1) return fail(SNK_EINVAL, "bad argument");
+  if (((uintptr_t)d_obs & 15) != 0) return fail(SNK_EINVAL, "rollout obs buffer must be 16-byte aligned");
+  const Params& p = h->p;
+  const size_t obs_step = (size_t)p.N * h->obs_out_env_bytes;
+  if (obs_step % 16 != 0 && T > 1) return fail(SNK_EINVAL, "N * obs bytes per env must be a multiple of 16 for a rollout");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int32_t t = 0; t < T; ++t) {
+    RolloutSlot slot;
+    slot.obs = d_obs + (size_t)t * obs_step;
+    slot.reward = d_reward ? d_reward + (size_t)t * p.N : nullptr;
+    slot.done = d_done ? d_done + (size_t)t * p.N : nullptr;
+    int rc = launch(h, MODE_STEP, d_actions + (size_t)t * p.N * p.S, nullptr, s, &slot);
+    if (rc) return rc;
+  }
+  // leave the handle's own buffers as after T calls of snk_step
+  RolloutSlot last;
+  last.obs = d_obs + (size_t)(T - 1) * obs_step;
+  CUDA_TRY(cudaMemcpyAsync(h->d_obs_user, last.obs, obs_step, cudaMemcpyDeviceToDevice, s));
+  if (d_reward) CUDA_TRY(cudaMemcpyAsync(p.reward, d_reward + (size_t)(T - 1) * p.N, (size_t)p.N * 4, cudaMemcpyDeviceToDevice, s));
+  if (d_done) CUDA_TRY(cudaMemcpyAsync(p.done, d_done + (size_t)(T - 1) * p.N, (size_t)p.N, cudaMemcpyDeviceToDevice, s));
+  return SNK_OK;
 }
 
 extern "C" int snk_step_host(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, float* h_reward, uint8_t* h_done,

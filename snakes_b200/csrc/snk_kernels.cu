@@ -204,7 +204,7 @@ __device__ __forceinline__ void store_image(const Params& p, const u8* tile, int
           bulk_store_s2g_hint(gdst + off, tile + off, (u32)min(16384, tile_bytes - off), pol);
       }
       bulk_commit();
-      if (!(p.debug & 16)) bulk_wait_read();
+      bulk_wait_read();
     }
   } else if (left >= p.TE) {
     const uint4* src = reinterpret_cast<const uint4*>(tile);
@@ -298,12 +298,12 @@ __global__ void __launch_bounds__(64) k_lane_paint(const Params p) {
     const long long next = item + stride;
     const PaintEnv<S> nxt = paint_env_from_memory<S>(p, next < n_items ? next * TE + slot : p.N);
     const long long e0 = item * TE;
-    if (!(p.debug & 1)) lane_paint<S, RULES, K, true>(p, cur, e0 + slot, sub, LPE, img);
+    lane_paint<S, RULES, K, true>(p, cur, e0 + slot, sub, LPE, img);
     fence_async_smem();
     __syncwarp();
-    if (!(p.debug & 2)) store_image(p, tile, tile_bytes, e0, lane);
+    store_image(p, tile, tile_bytes, e0, lane);
     __syncwarp();
-    if (!(p.debug & 1)) lane_paint<S, RULES, K, false>(p, cur, e0 + slot, sub, LPE, img);
+    lane_paint<S, RULES, K, false>(p, cur, e0 + slot, sub, LPE, img);
     __syncwarp();
     cur = nxt;
     item = next;

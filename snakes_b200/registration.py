@@ -69,7 +69,7 @@ class SnakeGymEnv(object):
         return obs[0].cpu().numpy(), float(rew[0]), bool(done[0]), info
 
     def render(self, mode="rgb_array"):
-        return self._venv.render(mode)
+        return self._venv.render(mode, 0)
 
     def close(self):
         if self._venv is not None:

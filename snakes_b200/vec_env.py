@@ -217,11 +217,28 @@ class SnakeVecEnv(object):
         except Exception:
             pass
 
-    def render(self, mode="rgb_array"):
-        """World view of env 0 (get_ob_world, snake_multiple_test.py:60-81): view 0 of the observation."""
+    _WORLD_COLOURS = (((0, 204, 0), (191, 242, 191)), ((0, 51, 204), (128, 154, 230)),
+                      ((204, 0, 119), (230, 128, 188)), ((119, 0, 204), (188, 128, 230)))
+
+    def render(self, mode="rgb_array", env_index=0):
+        """World view of one env as the reference's get_ob_world draws it (snake_multiple_test.py:60-91):
+        one [V, V, 3] uint8 image, fruit red, snake i in the i-th colour pair, white border.  It is
+        rebuilt on the host from the env's K views (snake k is the green one of view k), so it needs
+        K >= S and the native observation mode; there is no pyglet window on a GPU box."""
         if mode != "rgb_array":
-            raise NotImplementedError("only mode='rgb_array' (there is no pyglet viewer on a GPU box)")
-        return self.obs[0, :, :, 0:3].cpu().numpy()
+            raise NotImplementedError("only mode='rgb_array'")
+        if self.obs_mode != "native" or self.K < min(self.S, 4):
+            return self.obs[env_index, :, :, 0:3].cpu().numpy()
+        ob = self.obs[env_index].cpu().numpy().reshape(self.V, self.V, self.K, 3)
+        world = np.zeros((self.V, self.V, 3), dtype=np.uint8)
+        v0 = ob[:, :, 0]
+        world[(v0 == (255, 0, 0)).all(-1)] = (255, 0, 0)
+        for k in range(min(self.S, 4)):
+            body_c, head_c = self._WORLD_COLOURS[k]
+            world[(ob[:, :, k] == (0, 204, 0)).all(-1)] = body_c
+            world[(ob[:, :, k] == (191, 242, 191)).all(-1)] = head_c
+        world[(v0 == (255, 255, 255)).all(-1)] = (255, 255, 255)
+        return world
 
     @property
     def unwrapped(self):
@@ -236,6 +253,26 @@ class SnakeVecEnv(object):
             assert tensor.is_cuda and tensor.dtype == torch.uint8 and tensor.is_contiguous()
             _lib.check(self._L.snk_set_obs_target(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel()))
         self._bind_buffers()
+
+    def rollout(self, actions, obs_out=None, rewards_out=None, dones_out=None):
+        """T steps back to back into rollout buffers on the device (the mb_obs / mb_rewards /
+        mb_dones of Runner.run, ppo_multi_agent_new.py:178-198) with no host round trip.
+        actions: int8 CUDA tensor [T, N, S].  Returns (obs [T,N,H,W,3K] u8, rewards [T,N] f32, dones [T,N] bool)."""
+        a = torch.as_tensor(actions, device=self.device).to(torch.int8).contiguous()
+        T = int(a.shape[0])
+        assert tuple(a.shape) == (T, self.N, self.S)
+        shape = (T,) + tuple(self.obs.shape)
+        if obs_out is None:
+            obs_out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        if rewards_out is None:
+            rewards_out = torch.empty((T, self.N), dtype=torch.float32, device=self.device)
+        if dones_out is None:
+            dones_out = torch.empty((T, self.N), dtype=torch.uint8, device=self.device)
+        assert obs_out.is_contiguous() and tuple(obs_out.shape) == shape and obs_out.dtype == torch.uint8
+        _lib.check(self._L.snk_rollout(self._h, C.c_void_p(a.data_ptr()), T, C.c_void_p(obs_out.data_ptr()),
+                                       C.c_void_p(rewards_out.data_ptr()), C.c_void_p(dones_out.data_ptr()), self._stream()))
+        self._a_live = a
+        return obs_out, rewards_out, dones_out.view(torch.bool) if dones_out.dtype == torch.uint8 else dones_out
 
     def set_draw_tape(self, vals, bounds, offsets):
         """Replay mode: recorded reference draws, CSR per env (parity tests)."""

@@ -193,3 +193,48 @@ def test_checkpoint_resume_is_bit_exact(sb, tmp_path, rules, S, D):
     for k in s1:
         assert np.array_equal(s1[k], s2[k]), k
     env.close(); twin.close()
+
+
+@pytest.mark.parametrize("obs_mode,N", [("native", 256), ("atari84", 64), ("native", 100)])
+def test_rollout_writer_equals_step_by_step(sb, obs_mode, N):
+    """snk_rollout: T steps written straight into [T,N,...] buffers == T calls of step()."""
+    import torch
+    T = 12
+    kw = dict(size=19, n_snakes=2, seed=6, obs_mode=obs_mode)
+    a_env = sb.SnakeVecEnv(N, **kw)
+    b_env = sb.SnakeVecEnv(N, **kw)
+    a_env.reset(); b_env.reset()
+    acts = torch.stack([a_env.gen_actions(t, 2).clone() for t in range(T)])
+    if N % 8 != 0 and obs_mode == "native":
+        # 100 envs x 2646 B is not a multiple of 16: slots would be misaligned for the TMA store
+        with pytest.raises(sb.SnkError):
+            a_env.rollout(acts)
+        a_env.close(); b_env.close()
+        return
+    obs, rews, dones = a_env.rollout(acts)
+    for t in range(T):
+        o, r, d, _ = b_env.step(acts[t])
+        assert torch.equal(obs[t], o), t
+        assert torch.equal(rews[t], r) and torch.equal(dones[t], d), t
+    assert torch.equal(a_env.obs, b_env.obs) and torch.equal(a_env.rewards, b_env.rewards)
+    sa, sb_ = a_env.dump_state(), b_env.dump_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb_[k]), k
+    a_env.close(); b_env.close()
+
+
+def test_render_world_view(sb):
+    """render(mode='rgb_array') == the oracle's get_ob_world restatement, for every env index asked."""
+    import snake_oracle as so
+    N, S, D = 8, 3, 10
+    env = sb.SnakeVecEnv(N, size=D, n_snakes=S, seed=3)
+    orc = so.VecOracle(N, D, S, S, S, "classic", seed=3)
+    env.reset(); orc.reset()
+    for t in range(25):
+        a = env.gen_actions(t, 5).cpu().numpy()
+        env.step(a); orc.step(a)
+        for i in (0, 5):
+            img = env.render("rgb_array", env_index=i)
+            assert img.shape == (D + 2, D + 2, 3) and img.dtype == np.uint8
+            assert np.array_equal(img, orc.envs[i].world_view()), (t, i)
+    env.close()

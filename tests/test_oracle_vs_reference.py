@@ -65,3 +65,21 @@ def test_lockstep_scripted_policy(rules, S, D):
     import ref_compare
     max_len = ref_compare.lockstep_scripted(rules, S, D, 1500, seed=5)
     assert max_len >= 8
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("S,D", [(2, 19), (3, 10)])
+def test_world_view_matches_reference_get_ob_world(S, D):
+    """render(mode='rgb_array') source: get_ob_world (snake_multiple_test.py:60-91)."""
+    import ref_loader
+    ref = ref_loader.make_env("classic", S, D, np.random.RandomState(11))
+    orc = so.SnakeOracle(D, S, S, 3, "classic", draws=np.random.RandomState(11))
+    ref.reset(); orc.reset()
+    rng = np.random.RandomState(12)
+    for _ in range(300):
+        assert np.array_equal(ref.get_ob_world(), orc.world_view())
+        a = rng.randint(0, 5, size=S)
+        _, _, d, _ = ref.step(a)
+        orc.step(a)
+        if d:
+            ref.reset(); orc.reset()
