@@ -202,6 +202,7 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     // with 2646 B per env (2 views of 21x21) the image stream dominates and the fused form wins
     plan.ws = plan.kind == KIND_LANE && (lv ? !strcmp(lv, "ws") : p.E < 2048);
     plan.split = plan.kind == KIND_LANE && lv && !strcmp(lv, "split");
+    { const char* pd = getenv("SNK_PDL"); plan.pdl = !(pd && !strcmp(pd, "0")); }
     const char* lw = getenv("SNK_LOGIC_WARPS");
     p.PW = 2;
     logic_warps = lw ? atoi(lw) : 3;

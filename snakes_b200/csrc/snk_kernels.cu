@@ -421,6 +421,10 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   const bool stepping = p.mode == MODE_STEP;
   long long b = (long long)blockIdx.x * wpc + warp;
   LaneRaw<S> raw;
+  // Programmatic dependent launch: everything above (shared-memory carve-up, mbarrier, border image
+  // fetch) may overlap the tail of the previous launch in the stream; records, actions and every
+  // output are only touched after the previous grid has completed and flushed.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (b < n_batches && b * 32 + lane < p.N) raw = lane_fetch<S>(p, b * 32 + lane, stepping);
   bool have_image = false;
   for (; b < n_batches; b += stride) {
@@ -460,6 +464,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
     }
   }
   if (!have_image) mbar_wait(&s_bar[warp], 0);  // never leave with a bulk copy into our shared memory in flight
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next launch may start its prologue
   if (lane == 0) bulk_wait_all();
   reduce_lane_stats(p, st, errs, s_stats, lane);
   __syncthreads();
@@ -870,7 +875,14 @@ static cudaError_t launch_rules(const Params& p, const LaunchPlan& plan, cudaStr
     if (plan.ws) {                                                                                           \
       k_step_lane_ws<s, RULES, k><<<plan.grid, plan.block, plan.smem, stream>>>(p);                          \
     } else if (!plan.split) {                                                                                \
-      k_step_lane<s, RULES, k><<<plan.grid, plan.block, plan.smem, stream>>>(p);                             \
+      cudaLaunchConfig_t cfg = {};                                                                           \
+      cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(plan.block); cfg.dynamicSmemBytes = plan.smem;      \
+      cfg.stream = stream;                                                                                   \
+      cudaLaunchAttribute attr[1];                                                                           \
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                       \
+      attr[0].val.programmaticStreamSerializationAllowed = plan.pdl ? 1 : 0;                                 \
+      cfg.attrs = attr; cfg.numAttrs = 1;                                                                    \
+      return cudaLaunchKernelEx(&cfg, k_step_lane<s, RULES, k>, p);                                          \
     } else {                                                                                                 \
       if (p.mode != MODE_OBSERVE) k_lane_logic<s, RULES><<<(unsigned)((p.N + 127) / 128), 128, 0, stream>>>(p); \
       k_lane_paint<s, RULES, k><<<plan.grid, plan.block, plan.smem, stream>>>(p);                            \
