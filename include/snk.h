@@ -188,6 +188,13 @@ int snk_check_errors(snk_handle* h, uint32_t* flags, void* stream);
 int snk_gen_actions(snk_handle* h, int8_t* d_actions, uint64_t step, uint64_t seed,
                     int32_t n_actions, void* stream);
 
+/* Scripted policy for benchmarks (SURVEY.md section 8d second stream): every live snake turns toward
+ * its nearest fruit unless the next cell is a wall or a body cell, else keeps going; with probability
+ * eps_permille / 1000 a uniform random action instead (Philox stream 2).  Keeps snakes long (larger
+ * SigmaL, fewer resets).  Lane-family configurations with classic fruit lists only. */
+int snk_gen_scripted_actions(snk_handle* h, int8_t* d_actions, uint64_t step, uint64_t seed,
+                             int32_t eps_permille, void* stream);
+
 /* Algorithmic bytes of one env-step: obs K*H*W*3 + state 19S + 2*SigmaL + 2F + 30. */
 int snk_algorithmic_bytes_per_step(const snk_config* cfg, double mean_sum_len, double* out);
 

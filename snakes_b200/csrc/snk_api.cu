@@ -496,6 +496,16 @@ extern "C" int snk_gen_actions(snk_handle* h, int8_t* d_actions, uint64_t step, 
   return SNK_OK;
 }
 
+extern "C" int snk_gen_scripted_actions(snk_handle* h, int8_t* d_actions, uint64_t step, uint64_t seed, int32_t eps_permille, void* stream) {
+  if (!h || !d_actions || eps_permille < 0 || eps_permille > 1000) return fail(SNK_EINVAL, "bad argument");
+  if (h->p.family != 1 || h->cfg.rules != SNK_RULES_CLASSIC)
+    return fail(SNK_EINVAL, "the scripted policy needs a lane-family configuration with classic rules");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(snk_launch_scripted_actions(h->p, d_actions, step, seed, eps_permille, (cudaStream_t)stream));
+  h->launches++;
+  return SNK_OK;
+}
+
 extern "C" int snk_algorithmic_bytes_per_step(const snk_config* c, double mean_sum_len, double* out) {
   int rc = cfg_check(c);
   if (rc) return rc;

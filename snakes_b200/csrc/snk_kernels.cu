@@ -755,6 +755,47 @@ static cudaError_t launch_upscale(const uint8_t* native, uint8_t* out, long long
   return cudaGetLastError();
 }
 
+
+// k_scripted_actions: greedy fruit seeking on the device (benchmark action stream).  One thread per
+// env; occupancy = bitmap over padded cell ids in local memory, filled by walking the chain codes.
+template <int S>
+__global__ void __launch_bounds__(128) k_scripted_actions(const Params p, int8_t* actions, u64 step, u64 seed, int eps_permille) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.N) return;
+  LaneEnv<S> env;
+  lane_load<S>(p, e, env);
+  u32 occ[37];  // V*V <= 1156 bits
+  const int nW = (p.VV + 31) / 32, V = p.V, F = p.F;
+  for (int w = 0; w < nW; ++w) occ[w] = 0;
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+    chain_walk(env.head[s], env.len[s], env.c0[s], p.chain + (e * S + s) * p.CW, V, [&](int, int pid) { occ[pid >> 5] |= 1u << (pid & 31); });
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    int best = 0;
+    if (env.len[s]) {
+      const u32 rnd = philox_bounded(seed, (u64)(p.env_id_base + e), 2, step * (u64)S + (u64)s, 1000u * 5u);
+      if ((int)(rnd / 5u) < eps_permille) {
+        best = (int)(rnd % 5u);
+      } else {
+        int best_d = 0x7fffffff;
+        for (int a = 1; a <= 4; ++a) {
+          if (env.vel[s] && a == (((env.vel[s] + 1) & 3) + 1)) continue;  // reversal is ignored by the env anyway
+          const int c = env.head[s] + chain_delta((u32)(a - 1), V);
+          if ((__ldg(p.cellinfo + c) >> 31) || ((occ[c >> 5] >> (c & 31)) & 1)) continue;
+          const int cx = c / V, cy = c - cx * V;
+          int d = 0x7ffffffe;
+#pragma unroll
+          for (int f = 0; f < 4; ++f)
+            if (f < F) { const int fx = env.fruit[f] / V, fy = env.fruit[f] - fx * V; d = min(d, abs(cx - fx) + abs(cy - fy)); }
+          if (d < best_d) { best_d = d; best = a; }
+        }
+      }
+    }
+    actions[e * S + s] = (int8_t)best;
+  }
+}
+
 // ------------------------------------------------------------------ state dump / load, action stream
 // canonical blob <-> private layout; one thread per (env, snake); not on the hot path
 __global__ void k_dump(const Params p, u8* blob, snk_state_layout lay) {
@@ -986,6 +1027,17 @@ cudaError_t snk_launch_dump(const Params& p, u8* blob, const snk_state_layout& l
 cudaError_t snk_launch_load(const Params& p, const u8* blob, const snk_state_layout& lay, cudaStream_t stream) {
   const long long n = p.N * p.S;
   k_load<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, blob, lay);
+  return cudaGetLastError();
+}
+
+cudaError_t snk_launch_scripted_actions(const Params& p, int8_t* actions, u64 step, u64 seed, int eps_permille, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((p.N + 127) / 128);
+  switch (p.S) {
+    case 1: k_scripted_actions<1><<<grid, 128, 0, stream>>>(p, actions, step, seed, eps_permille); break;
+    case 2: k_scripted_actions<2><<<grid, 128, 0, stream>>>(p, actions, step, seed, eps_permille); break;
+    case 3: k_scripted_actions<3><<<grid, 128, 0, stream>>>(p, actions, step, seed, eps_permille); break;
+    default: k_scripted_actions<4><<<grid, 128, 0, stream>>>(p, actions, step, seed, eps_permille); break;
+  }
   return cudaGetLastError();
 }
 

@@ -322,6 +322,14 @@ class SnakeVecEnv(object):
                                            self.action_space.n, self._stream()))
         return out
 
+    def gen_scripted_actions(self, step, seed=1, eps=0.05, out=None):
+        """Benchmark policy computed on the device from the current state: turn toward the nearest
+        fruit unless the next cell is a wall or a body, with probability `eps` a random action."""
+        out = self._actions if out is None else out
+        _lib.check(self._L.snk_gen_scripted_actions(self._h, C.c_void_p(out.data_ptr()), int(step), int(seed),
+                                                    int(round(eps * 1000)), self._stream()))
+        return out
+
     def stats(self, reduce=True):
         """Running episode statistics (Monitor's aggregate role).  With torch.distributed
         initialised and reduce=True the 8 doubles are summed over all ranks (NCCL all-reduce):

@@ -361,3 +361,24 @@ def test_cut_equals_classic_without_strikes_full_size(sb):
     for k in ("t", "len", "grow_to", "vel", "body", "draw_ctr"):
         assert np.array_equal(sa[k], sb_[k]), k
     a_env.close(); b_env.close()
+
+
+def test_scripted_policy_stream_vs_oracle(sb):
+    """The on-device fruit-seeking policy (bench.py's second action stream) keeps snakes long; the
+    env under it stays bit-exact with the oracle fed the same actions."""
+    N = 512
+    kw = dict(size=19, n_snakes=2, rules="classic", seed=8)
+    env = sb.SnakeVecEnv(N, **kw)
+    co = c_oracle.COracle(N, **kw)
+    assert np.array_equal(env.reset().cpu().numpy(), co.reset())
+    longest = 0
+    for t in range(600):
+        a = env.gen_scripted_actions(t, seed=3, eps=0.05).cpu().numpy()
+        assert a.min() >= 0 and a.max() <= 4
+        _compare_step(env, co, a, "scripted stream step %d" % t, check_state=(t % 50 == 0))
+        if t % 50 == 0:
+            longest = max(longest, int(co.state()["len"].max()))
+    assert longest >= 25
+    s = env.stats(reduce=False)
+    assert s["body_cells"] / s["env_steps"] > 8.0  # random policy: about 4.3
+    env.close()
