@@ -170,7 +170,7 @@ def run_reference(args):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.005):
         threading.Thread.__init__(self, daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.stop_flag, self.max_mhz = [], set(), False, None
@@ -226,6 +226,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SNK_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
