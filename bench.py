@@ -217,6 +217,11 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------ this repo's CUDA path
 def run_ours(args):
+    # stdout carries exactly ONE JSON line: everything libraries print (the NCCL version banner goes
+    # to fd 1) is sent to stderr, the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import snakes_b200
@@ -370,7 +375,8 @@ def run_ours(args):
                           % (n, cores, dts, cpu_model()),
                 "c_oracle_1core": time_c_oracle(2.0) * S,
             }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     env.close(); henv.close()
     if world > 1:
         dist.destroy_process_group()
