@@ -166,6 +166,16 @@ int snk_set_obs_target(snk_handle* h, uint8_t* d_obs, size_t bytes);
 int snk_rollout(snk_handle* h, const int8_t* d_actions, int32_t T, uint8_t* d_obs, float* d_reward,
                 uint8_t* d_done, void* stream);
 
+/* Generalised advantage estimation over a rollout, on the device (the numpy loop at the end of
+ * Runner.run, ppo_multi_agent_new.py:205-218), bit-exact with that loop's mixed precision: float32
+ * inputs, gamma * next_value in float32, everything else in float64, advantages rounded to float32,
+ * returns = advs + values in float32.  d_dones[t] is the done flag BEFORE step t (mb_dones[t]);
+ * d_last_dones / d_last_values are the flags / value estimates after the last step.  All arrays
+ * [T][N] (or [N]) on `device`.  Not tied to a handle. */
+int snk_gae(const float* d_rewards, const float* d_values, const uint8_t* d_dones, const float* d_last_values,
+            const uint8_t* d_last_dones, double gamma, double lam, int32_t T, int64_t N, float* d_advs,
+            float* d_returns, int32_t device, void* stream);
+
 /* Replay mode: per-env tapes of the reference's np_random.randint draws
  * (snake_multiple_test.py:200, :215).  CSR: env i owns vals/bounds[offsets[i] .. offsets[i+1]).
  * Host arrays, copied to the device (synchronous).  Switches the handle to SNK_RNG_TAPE. */

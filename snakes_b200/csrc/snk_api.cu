@@ -506,6 +506,17 @@ extern "C" int snk_gen_scripted_actions(snk_handle* h, int8_t* d_actions, uint64
   return SNK_OK;
 }
 
+extern "C" int snk_gae(const float* d_rewards, const float* d_values, const uint8_t* d_dones, const float* d_last_values,
+                       const uint8_t* d_last_dones, double gamma, double lam, int32_t T, int64_t N, float* d_advs, float* d_returns,
+                       int32_t device, void* stream) {
+  if (!d_rewards || !d_values || !d_dones || !d_last_values || !d_last_dones || !d_advs || !d_returns || T < 1 || N < 1)
+    return fail(SNK_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(snk_launch_gae(d_rewards, d_values, d_dones, d_last_values, d_last_dones, gamma, lam, T, N, d_advs, d_returns,
+                          (cudaStream_t)stream));
+  return SNK_OK;
+}
+
 extern "C" int snk_algorithmic_bytes_per_step(const snk_config* c, double mean_sum_len, double* out) {
   int rc = cfg_check(c);
   if (rc) return rc;

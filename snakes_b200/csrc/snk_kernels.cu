@@ -796,6 +796,33 @@ __global__ void __launch_bounds__(128) k_scripted_actions(const Params p, int8_t
   }
 }
 
+
+// k_gae: the reversed GAE loop of Runner.run (ppo_multi_agent_new.py:209-218), one thread per env.
+// The reference mixes precisions (float32 arrays, `1.0 - dones` is float64, python-float gamma): every
+// operation below is the same IEEE operation in the same order, with explicit _rn intrinsics so that
+// nothing is contracted into an FMA.
+__global__ void k_gae(const float* __restrict__ rewards, const float* __restrict__ values, const u8* __restrict__ dones,
+                      const float* __restrict__ last_values, const u8* __restrict__ last_dones, double gamma, double lam, int T,
+                      long long N, float* __restrict__ advs, float* __restrict__ returns) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float gamma32 = (float)gamma;          // python float * float32 array -> float32 product
+  const double gl = __dmul_rn(gamma, lam);     // python float * python float
+  double last = 0.0;
+  for (int t = T - 1; t >= 0; --t) {
+    const bool tail = t == T - 1;
+    const double nonterm = __dsub_rn(1.0, (double)(tail ? last_dones[n] : dones[(long long)(t + 1) * N + n]));
+    const float nextv = tail ? last_values[n] : values[(long long)(t + 1) * N + n];
+    const float v = values[(long long)t * N + n];
+    const double gvn = __dmul_rn((double)__fmul_rn(gamma32, nextv), nonterm);
+    const double delta = __dsub_rn(__dadd_rn((double)rewards[(long long)t * N + n], gvn), (double)v);
+    last = __dadd_rn(delta, __dmul_rn(__dmul_rn(gl, nonterm), last));
+    const float a = (float)last;
+    advs[(long long)t * N + n] = a;
+    returns[(long long)t * N + n] = __fadd_rn(a, v);
+  }
+}
+
 // ------------------------------------------------------------------ state dump / load, action stream
 // canonical blob <-> private layout; one thread per (env, snake); not on the hot path
 __global__ void k_dump(const Params p, u8* blob, snk_state_layout lay) {
@@ -1038,6 +1065,13 @@ cudaError_t snk_launch_scripted_actions(const Params& p, int8_t* actions, u64 st
     case 3: k_scripted_actions<3><<<grid, 128, 0, stream>>>(p, actions, step, seed, eps_permille); break;
     default: k_scripted_actions<4><<<grid, 128, 0, stream>>>(p, actions, step, seed, eps_permille); break;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t snk_launch_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                           const uint8_t* last_dones, double gamma, double lam, int T, long long N, float* advs, float* returns,
+                           cudaStream_t stream) {
+  k_gae<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(rewards, values, dones, last_values, last_dones, gamma, lam, T, N, advs, returns);
   return cudaGetLastError();
 }
 

@@ -26,5 +26,8 @@ cudaError_t snk_launch_upscale84(const uint8_t* native, uint8_t* out, long long 
 cudaError_t snk_launch_dump(const Params& p, uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);
 cudaError_t snk_launch_load(const Params& p, const uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);
 cudaError_t snk_launch_scripted_actions(const Params& p, int8_t* actions, uint64_t step, uint64_t seed, int eps_permille, cudaStream_t stream);
+cudaError_t snk_launch_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                           const uint8_t* last_dones, double gamma, double lam, int T, long long N, float* advs, float* returns,
+                           cudaStream_t stream);
 cudaError_t snk_launch_gen_actions(int8_t* actions, long long N, int S, long long env_id_base, uint64_t step,
                                    uint64_t seed, int n_actions, cudaStream_t stream);

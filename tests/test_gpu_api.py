@@ -238,3 +238,23 @@ def test_render_world_view(sb):
             assert img.shape == (D + 2, D + 2, 3) and img.dtype == np.uint8
             assert np.array_equal(img, orc.envs[i].world_view()), (t, i)
     env.close()
+
+
+@pytest.mark.parametrize("T,N,gamma,lam", [(64, 1000, 0.99, 0.95), (5, 33, 0.9, 1.0), (1, 7, 0.99, 0.95), (128, 4096, 0.999, 0.9)])
+def test_gae_on_device_is_bit_exact(sb, T, N, gamma, lam):
+    """snk_gae == the numpy loop of Runner.run (ppo_multi_agent_new.py:205-218), bit for bit."""
+    import torch
+    import gae_oracle
+    rng = np.random.RandomState(T + N)
+    rewards = rng.choice([-1.0, 0.0, 0.0, 0.0, 1.0, 2.0], size=(T, N)).astype(np.float32)
+    values = rng.randn(T, N).astype(np.float32) * 3
+    dones = rng.rand(T, N) < 0.1
+    last_values = rng.randn(N).astype(np.float32)
+    last_dones = rng.rand(N) < 0.1
+    want_a, want_r = gae_oracle.gae(rewards, values, dones, last_values, last_dones, gamma, lam)
+    dev = torch.device("cuda", 0)
+    t = lambda x: torch.as_tensor(x, device=dev)
+    got_a, got_r = sb.gae(t(rewards), t(values), t(dones), t(last_values), t(last_dones), gamma, lam)
+    assert got_a.dtype == torch.float32 and tuple(got_a.shape) == (T, N)
+    assert np.array_equal(got_a.cpu().numpy().view(np.uint32), want_a.view(np.uint32))
+    assert np.array_equal(got_r.cpu().numpy().view(np.uint32), want_r.view(np.uint32))
