@@ -89,6 +89,11 @@ CONFIGS = [
     ("classic", 1, 10, 1, 3, 33, 200),       # more views than snakes
     ("classic", 4, 7, 6, 2, 300, 300),       # F > S, K < S
     ("classic", 2, 10, 4, 2, 500, 300),      # NewMultipleSnakes defaults: 2 snakes, 4 fruits
+    ("classic", 2, 10, 0, 2, 200, 200),      # no fruit at all
+    ("classic", 4, 19, 4, 4, 300, 200),      # 4 snakes, 4 views on 19x19: 42 KB image per warp
+    ("cut", 4, 19, 4, 4, 200, 200),
+    ("classic", 2, 2, 2, 2, 300, 200),       # smallest board
+    ("adversarial", 3, 32, 3, 3, 64, 150),   # largest board of the lane kernel class
     ("classic", 3, 3, 3, 3, 256, 300),       # crowded board: no-free-cell + alias paths
     ("adversarial", 3, 10, 3, 3, 500, 400),
     ("adversarial", 2, 5, 2, 2, 129, 400),
@@ -381,4 +386,21 @@ def test_scripted_policy_stream_vs_oracle(sb):
     assert longest >= 25
     s = env.stats(reduce=False)
     assert s["body_cells"] / s["env_steps"] > 8.0  # random policy: about 4.3
+    env.close()
+
+
+def test_time_limit_episodes(sb):
+    """max_steps: done by the step cap (reference: t >= 2000, snake_multiple_test.py:195), reward 0."""
+    N = 256
+    kw = dict(size=19, n_snakes=2, seed=12, max_steps=6)
+    env = sb.SnakeVecEnv(N, **kw)
+    co = c_oracle.COracle(N, **kw)
+    assert np.array_equal(env.reset().cpu().numpy(), co.reset())
+    capped = 0
+    for t in range(40):
+        a = np.zeros((N, 2), dtype=np.int8)  # nobody moves: only spawn overlaps and the cap end episodes
+        _compare_step(env, co, a, "cap step %d" % t)
+        d = env._done_u8.cpu().numpy().astype(bool)
+        capped += int((d & (env.rewards.cpu().numpy() == 0)).sum())
+    assert capped >= N * 5
     env.close()
