@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsnk.so")
+LIB_PATH = os.environ.get("SNK_LIB") or os.path.join(_HERE, "libsnk.so")  # SNK_LIB: A/B builds during kernel work
 
 RULES = {"classic": 0, "adversarial": 1, "cut": 2}
 OBS_NATIVE, OBS_ATARI84 = 0, 1

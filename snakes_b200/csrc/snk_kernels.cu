@@ -661,6 +661,13 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
   if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
+// The file can be compiled as one translation unit (SNK_TU undefined) or as four that build in
+// parallel: SNK_TU = 0 / 1 / 2 instantiates the step kernels of one rule-set, SNK_TU = 3 holds the
+// remaining kernels and the host dispatch.
+#ifndef SNK_TU
+#define SNK_TU (-1)
+#endif
+#if SNK_TU == -1 || SNK_TU == 3
 // k_upscale84: obs_mode = SNK_OBS_ATARI84, the reference's WarpFrame (utils.py:27-31):
 // cv2.resize(frame, (84, 84), INTER_AREA), which for 84 % V == 0 is exact r x r pixel replication
 // (r = 84 / V).  One CTA per env: the native [V][V][3K] image is staged in shared memory, every
@@ -924,19 +931,27 @@ __global__ void k_gen_actions(int8_t* actions, long long N, int S, long long env
   actions[i] = (int8_t)philox_bounded(seed, (u64)(env_id_base + e), 1, step * (u64)S + (u64)s, (u32)n_actions);
 }
 
+#endif  // misc kernels
+
 // ------------------------------------------------------------------ launchers
 // (S, K) pairs the lane kernel is compiled for: one view per snake, or the 3 views SnakeEnv emits
+#ifdef LANE_COMBOS_OVERRIDE  // quick A/B builds (tools/build_variant.sh): the two bench shapes only
+#define LANE_COMBOS(X) X(2, 2) X(3, 3)
+#else
 #define LANE_COMBOS(X) X(1, 1) X(2, 2) X(3, 3) X(4, 4) X(1, 3) X(2, 3)
+#endif
 
+#if SNK_TU == -1 || SNK_TU == 3
 bool snk_lane_supported(int S, int K) {
 #define X(s, k) if (S == s && K == k) return true;
   LANE_COMBOS(X)
 #undef X
   return false;
 }
+#endif
 
 template <int RULES>
-static cudaError_t launch_rules(const Params& p, const LaunchPlan& plan, cudaStream_t stream) {
+cudaError_t launch_rules(const Params& p, const LaunchPlan& plan, cudaStream_t stream) {
   if (plan.kind == KIND_LANE) {
 #define X(s, k)                                                                                              \
   if (p.S == s && p.K == k) {                                                                                \
@@ -974,6 +989,14 @@ static cudaError_t launch_rules(const Params& p, const LaunchPlan& plan, cudaStr
   return cudaGetLastError();
 }
 
+#if SNK_TU >= 0 && SNK_TU <= 2
+template cudaError_t launch_rules<SNK_TU>(const Params&, const LaunchPlan&, cudaStream_t);
+#elif SNK_TU == 3
+extern template cudaError_t launch_rules<SNK_RULES_CLASSIC>(const Params&, const LaunchPlan&, cudaStream_t);
+extern template cudaError_t launch_rules<SNK_RULES_ADVERSARIAL>(const Params&, const LaunchPlan&, cudaStream_t);
+extern template cudaError_t launch_rules<SNK_RULES_CUT>(const Params&, const LaunchPlan&, cudaStream_t);
+#endif
+#if SNK_TU == -1 || SNK_TU == 3
 cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, cudaStream_t stream) {
   switch (rules) {
     case SNK_RULES_CLASSIC: return launch_rules<SNK_RULES_CLASSIC>(p, plan, stream);
@@ -981,6 +1004,8 @@ cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, 
     default: return launch_rules<SNK_RULES_CUT>(p, plan, stream);
   }
 }
+
+#endif
 
 template <int S, int RULES, int K>
 static cudaError_t plan_lane(LaunchPlan& plan, int& occ) {
@@ -998,7 +1023,7 @@ static cudaError_t plan_lane(LaunchPlan& plan, int& occ) {
 }
 
 template <int RULES>
-static cudaError_t plan_rules(LaunchPlan& plan, int n_sm, int S, int K) {
+cudaError_t plan_rules(LaunchPlan& plan, int n_sm, int S, int K) {
   cudaError_t err = cudaErrorInvalidConfiguration;
   int occ = 0;
   if (plan.kind == KIND_LANE) {
@@ -1025,6 +1050,14 @@ static cudaError_t plan_rules(LaunchPlan& plan, int n_sm, int S, int K) {
   return cudaSuccess;
 }
 
+#if SNK_TU >= 0 && SNK_TU <= 2
+template cudaError_t plan_rules<SNK_TU>(LaunchPlan&, int, int, int);
+#elif SNK_TU == 3
+extern template cudaError_t plan_rules<SNK_RULES_CLASSIC>(LaunchPlan&, int, int, int);
+extern template cudaError_t plan_rules<SNK_RULES_ADVERSARIAL>(LaunchPlan&, int, int, int);
+extern template cudaError_t plan_rules<SNK_RULES_CUT>(LaunchPlan&, int, int, int);
+#endif
+#if SNK_TU == -1 || SNK_TU == 3
 cudaError_t snk_plan(int rules, LaunchPlan& plan, int n_sm, int S, int K) {
   switch (rules) {
     case SNK_RULES_CLASSIC: return plan_rules<SNK_RULES_CLASSIC>(plan, n_sm, S, K);
@@ -1081,3 +1114,4 @@ cudaError_t snk_launch_gen_actions(int8_t* actions, long long N, int S, long lon
   k_gen_actions<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(actions, N, S, env_id_base, step, seed, n_actions);
   return cudaGetLastError();
 }
+#endif  // host dispatch

@@ -48,33 +48,15 @@ __device__ __forceinline__ int chain_delta(u32 d, int V) {  // d = vel-1: +V, +1
   return (d & 2) ? -dv : dv;
 }
 
-// The first four chain words of a body (65 segments) fetched up front with independent loads, so
-// that walks and position look-ups do not pay one dependent L2 round trip per 16 segments.
-struct ChainWords {
-  u32 w[4];
-};
-__device__ __forceinline__ ChainWords chain_fetch(u32 c0, const u32* __restrict__ ch, int len) {
-  ChainWords c;
-  c.w[0] = c0;
-  c.w[1] = len > 17 ? ch[1] : 0u;
-  c.w[2] = len > 33 ? ch[2] : 0u;
-  c.w[3] = len > 49 ? ch[3] : 0u;
-  return c;
-}
-__device__ __forceinline__ u32 chain_word(const ChainWords& c, const u32* __restrict__ ch, int k) {
-  return k == 0 ? c.w[0] : k == 1 ? c.w[1] : k == 2 ? c.w[2] : k == 3 ? c.w[3] : ch[k];
-}
-
 // visit(i, pid) for every segment, head first
 template <class Fn>
 __device__ __forceinline__ void chain_walk(int head, int len, u32 c0, const u32* __restrict__ ch, int V, Fn visit) {
-  const ChainWords cw = chain_fetch(c0, ch, len);
   int pid = head;
   u32 w = c0;
   for (int i = 0; i < len; ++i) {
     visit(i, pid);
     const int j = i & 15;
-    if (j == 0 && i) w = chain_word(cw, ch, i >> 4);
+    if (j == 0 && i) w = ch[i >> 4];
     pid -= chain_delta((w >> (2 * j)) & 3, V);
   }
 }
@@ -230,10 +212,9 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<
     {  // push the new direction: segment 0 -> 1 was created by `vel`
       u32* ch = p.chain + (e * S + s) * p.CW;
       const int nw = (len - 1 + 15) >> 4;
-      const ChainWords cw = chain_fetch(env.c0[s], ch, nw > 1 ? 16 * nw + 1 : 0);  // words 1..3 in one go
       u32 carry = env.c0[s] >> 30;
       env.c0[s] = (env.c0[s] << 2) | (u32)(vel - 1);
-      for (int k = 1; k < nw; ++k) { const u32 w = chain_word(cw, ch, k); ch[k] = (w << 2) | carry; carry = w >> 30; }
+      for (int k = 1; k < nw; ++k) { const u32 w = ch[k]; ch[k] = (w << 2) | carry; carry = w >> 30; }
     }
     env.head[s] = head; env.len[s] = len; env.grow[s] = grow; env.vel[s] = vel;
     if (RULES == SNK_RULES_CLASSIC) {
@@ -436,16 +417,16 @@ __device__ __forceinline__ void lane_store(const Params& p, long long e, const L
 
 // Position of segment i without walking: the 2-bit codes before it are counted per direction with
 // popcounts, pid_i = head - V*(#(+V) - #(-V)) - (#(+1) - #(-1)).
-__device__ __forceinline__ int chain_pos(int head, const ChainWords& cw, const u32* __restrict__ ch, int V, int i) {
+__device__ __forceinline__ int chain_pos(int head, u32 c0, const u32* __restrict__ ch, int V, int i) {
   int nV = 0, n1 = 0;
+  u32 w = c0;
   int k = 0;
   for (; i - 16 * k > 16; ++k) {  // whole words before the one holding code i-1 (bodies longer than 17)
-    const u32 w = chain_word(cw, ch, k);
     const u32 lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
     nV += 16 - __popc(lo | hi) - __popc(hi & ~lo);
     n1 += __popc(lo & ~hi) - __popc(lo & hi);
+    w = ch[k + 1];
   }
-  const u32 w = chain_word(cw, ch, k);
   const int r = i - 16 * k;  // 0..16 codes of word k
   const u32 m = r >= 16 ? 0x55555555u : ((1u << (2 * r)) - 1u) & 0x55555555u;
   const u32 lo = w & m, hi = (w >> 1) & m;
@@ -546,8 +527,7 @@ __device__ __forceinline__ void lane_paint(const Params& p, const PaintEnv<S>& p
   for (int s = 0; s < S; ++s) {
     if (pe.valid) {
       const u32* ch = p.chain + (e_owner * S + s) * p.CW;
-      const ChainWords cw = chain_fetch(pe.c0[s], ch, pe.len[s]);
-      for (int i = sub; i < pe.len[s]; i += LPE) put_pixel<S, K, PAINT>(img + chain_pos(pe.head[s], cw, ch, V, i) * C, s, i == 0);
+      for (int i = sub; i < pe.len[s]; i += LPE) put_pixel<S, K, PAINT>(img + chain_pos(pe.head[s], pe.c0[s], ch, V, i) * C, s, i == 0);
     }
     if (PAINT) __syncwarp();
   }
