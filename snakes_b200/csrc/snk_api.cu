@@ -200,7 +200,10 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     // measured on B200: with a small image per env (3 views of 12x12: 1296 B) the step is bound by the
     // logic's latency and the warp-specialised form (more logic warps per image buffer) is 1.4x faster;
     // with 2646 B per env (2 views of 21x21) the image stream dominates and the fused form wins
-    plan.ws = plan.kind == KIND_LANE && (lv ? !strcmp(lv, "ws") : p.E < 2048);
+    // ... unless there are too few 32-env batches to give every SM a few (4 096 envs of 2x10x10: one
+    // batch per SM at most): then a warp that steps AND paints its batch has the shortest critical path
+    // (13.8 us vs 19.0 us per step)
+    plan.ws = plan.kind == KIND_LANE && (lv ? !strcmp(lv, "ws") : (p.E < 2048 && (N + 31) / 32 >= 2LL * h->n_sm));
     plan.split = plan.kind == KIND_LANE && lv && !strcmp(lv, "split");
     { const char* pd = getenv("SNK_PDL"); plan.pdl = !(pd && !strcmp(pd, "0")); }
     const char* lw = getenv("SNK_LOGIC_WARPS");

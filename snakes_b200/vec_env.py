@@ -29,6 +29,18 @@ def _alias(ptr, shape, typestr, device):
     return torch.as_tensor(_DevPtr(ptr, shape, typestr), device=device)
 
 
+def tile_images(img_nhwc):
+    """N images -> one P x Q mosaic, P = ceil(sqrt(N)), Q = ceil(N / P), missing tiles black
+    (the layout of baselines/common/tile_images.py:3-22)."""
+    img = np.asarray(img_nhwc)
+    n, h, w, c = img.shape
+    P = int(np.ceil(np.sqrt(n)))
+    Q = int(np.ceil(float(n) / P))
+    canvas = np.zeros((P * Q, h, w, c), dtype=img.dtype)
+    canvas[:n] = img
+    return canvas.reshape(P, Q, h, w, c).transpose(0, 2, 1, 3, 4).reshape(P * h, Q * w, c)
+
+
 class Infos(object):
     """Lazily materialised `infos` of one step: behaves like the tuple of per-env dicts that
     SubprocVecEnv returns ({'ale.lives': 1, 'num_snakes': n[, 'episode': {'r','l','t'}]},
@@ -239,6 +251,15 @@ class SnakeVecEnv(object):
             world[(ob[:, :, k] == (191, 242, 191)).all(-1)] = head_c
         world[(v0 == (255, 255, 255)).all(-1)] = (255, 255, 255)
         return world
+
+    def get_images(self):
+        """VecEnv.get_images (baselines/common/vec_env/__init__.py): the world view of every env, [N, V, V, 3]."""
+        return np.stack([self.render("rgb_array", i) for i in range(self.N)])
+
+    def render_tiled(self, max_envs=64):
+        """VecEnv.render's big image: the first `max_envs` world views tiled into one P x Q mosaic."""
+        n = min(self.N, max_envs)
+        return tile_images(np.stack([self.render("rgb_array", i) for i in range(n)]))
 
     @property
     def unwrapped(self):

@@ -17,11 +17,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def sass_lines(kernel_sub):
-    tmp = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "snakes_b200", "libsnk.so")], cwd=tmp,
-                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    out = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, "snk_kernels.sm_100a.cubin")],
-                         capture_output=True, text=True).stdout
+    # the library is linked from several objects whose cubins share one name: disassemble per object
+    bdir = os.path.join(ROOT, "snakes_b200", "csrc", "_build")
+    objs = sorted(os.path.join(bdir, f) for f in os.listdir(bdir) if f.endswith(".o")) if os.path.isdir(bdir) else []
+    out = ""
+    for obj in objs or [os.path.join(ROOT, "snakes_b200", "libsnk.so")]:
+        tmp = tempfile.mkdtemp()
+        subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for f in sorted(os.listdir(tmp)):
+            if f.endswith(".cubin"):
+                out += subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, f)], capture_output=True, text=True).stdout
     funcs, cur, line = {}, None, None
     for l in out.splitlines():
         m = re.match(r"\s*\.text\.(\S+):", l)
