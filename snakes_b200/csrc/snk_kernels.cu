@@ -427,7 +427,13 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (b < n_batches && b * 32 + lane < p.N) raw = lane_fetch<S>(p, b * 32 + lane, stepping);
   bool have_image = false;
+#ifdef SNK_PHASE_TIMING  // experiment build (tools/phase.py): cycles per phase, summed over warps
+  long long tA = 0, tB = 0, tC = 0, tD = 0; const long long tStart = clock64();
+#endif
   for (; b < n_batches; b += stride) {
+#ifdef SNK_PHASE_TIMING
+    long long t0 = clock64();
+#endif
     const long long e = b * 32 + lane;
     const bool valid = e < p.N;
     LaneEnv<S> env;
@@ -450,6 +456,9 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
     if (b + stride < n_batches && (b + stride) * 32 + lane < p.N) raw = lane_fetch<S>(p, (b + stride) * 32 + lane, stepping);
     if (!have_image) { mbar_wait(&s_bar[warp], 0); have_image = true; }
     __syncwarp();  // chain words / fruit grid written by the owner lane are read by the painting lanes
+#ifdef SNK_PHASE_TIMING
+    { const long long t1 = clock64(); tA += t1 - t0; t0 = t1; }
+#endif
     for (int q = 0; q < LPE; ++q) {
       const long long e0 = b * 32 + (long long)q * TE;
       if (e0 >= p.N) break;
@@ -457,12 +466,28 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
       lane_paint<S, RULES, K, true>(p, pe, e0 + slot, sub, LPE, img);
       fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
       __syncwarp();
+#ifdef SNK_PHASE_TIMING
+      { const long long t1 = clock64(); tB += t1 - t0; t0 = t1; }
+#endif
       store_image(p, tile, tile_bytes, e0, lane);
       __syncwarp();
+#ifdef SNK_PHASE_TIMING
+      { const long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
+#endif
       lane_paint<S, RULES, K, false>(p, pe, e0 + slot, sub, LPE, img);
       __syncwarp();
+#ifdef SNK_PHASE_TIMING
+      { const long long t1 = clock64(); tD += t1 - t0; t0 = t1; }
+#endif
     }
   }
+#ifdef SNK_PHASE_TIMING
+  if (lane == 0) {  // the last five statistics carry the cycle sums instead (total, logic, paint, store + wait, un-paint)
+    atomicAdd(&p.stats[3], (double)(clock64() - tStart)); atomicAdd(&p.stats[4], (double)tA); atomicAdd(&p.stats[5], (double)tB);
+    atomicAdd(&p.stats[6], (double)tC); atomicAdd(&p.stats[7], (double)tD);
+  }
+  st.len_sum = st.fruits = st.deaths = st.cells = st.draws = 0.f;
+#endif
   if (!have_image) mbar_wait(&s_bar[warp], 0);  // never leave with a bulk copy into our shared memory in flight
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next launch may start its prologue
   if (lane == 0) bulk_wait_all();
@@ -543,6 +568,61 @@ __device__ __forceinline__ void pattern3(u32 rgb, u32& w0, u32& w1, u32& w2) {  
 
 __device__ __forceinline__ void consumer_sync(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 
+// One cell code -> the C bytes of its pixel in a chunk buffer (16-byte vector stores).  CT = compile-time
+// pixel size (48 = 16 views, the large-field configuration: the per-word phase of the RGB pattern and the
+// store loop then fold to constants), 0 = run time.
+template <int CT>
+__device__ __forceinline__ void rows_emit(u8* __restrict__ tile, int i, int cd, int C_, int K) {
+  const int C = CT > 0 ? CT : C_;
+  u32 rgb = 0;
+  int self = -1;
+  if (cd == 1) rgb = 255u;
+  else if (cd == 255) rgb = 0xffffffu;
+  else if (cd >= 3) { self = (cd - 3) >> 1; rgb = snake_rgb(false, (cd - 3) & 1); }
+  u32 w0, w1, w2;
+  pattern3(rgb, w0, w1, w2);
+  u8* px = tile + i * C;
+  if ((C & 15) == 0) {
+    uint4* q = reinterpret_cast<uint4*>(px);
+    const int n16 = C / 16;
+#pragma unroll
+    for (int j = 0; j < n16; ++j) {  // word index 4j: period 3 words
+      const int ph = (4 * j) % 3;
+      const u32 a0 = ph == 0 ? w0 : ph == 1 ? w1 : w2, a1 = ph == 0 ? w1 : ph == 1 ? w2 : w0, a2 = ph == 0 ? w2 : ph == 1 ? w0 : w1;
+      q[j] = make_uint4(a0, a1, a2, a0);
+    }
+  } else {
+    for (int j = 0; j < C; ++j) px[j] = (u8)(rgb >> (8 * (j % 3)));
+  }
+  if (self >= 0 && self < K) {
+    const u32 own = snake_rgb(true, (cd - 3) & 1);
+    px[3 * self] = (u8)own; px[3 * self + 1] = (u8)(own >> 8); px[3 * self + 2] = (u8)(own >> 16);
+  }
+}
+
+// Expand the `cells` cell codes of one chunk, one thread per cell.
+template <int RULES, int CT>
+__device__ __forceinline__ void rows_expand(const u8* __restrict__ code, const u8* __restrict__ fgrid, u8* __restrict__ tile,
+                                            int cells, int C, int K, int ct, int cn) {
+  if (RULES == SNK_RULES_CLASSIC) {
+    for (int i = ct; i < cells; i += cn) rows_emit<CT>(tile, i, code[i], C, K);
+  } else {
+    // count-grid rules: the fruit counts of four cells are fetched from HBM / L2 before any of them is
+    // expanded (one memory round trip per four cells instead of one per cell)
+    for (int i0 = ct; i0 < cells; i0 += 4 * cn) {
+      int cdv[4];
+      u8 fv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int i = i0 + k * cn; cdv[k] = i < cells ? (int)code[i] : -1; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) fv[k] = cdv[k] == 0 ? fgrid[i0 + k * cn] : (u8)0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (cdv[k] >= 0) rows_emit<CT>(tile, i0 + k * cn, fv[k] ? 1 : cdv[k], C, K);  // fruit: lowest paint priority
+    }
+  }
+}
+
 template <int RULES>
 __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
   extern __shared__ __align__(128) u8 smem[];
@@ -560,6 +640,9 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
   u32 errs = 0;
   const int n_chunks = (V + R - 1) / R;
   int issued = 0;  // chunks handed to the TMA engine so far (bulk groups of the consumers' thread 0)
+#ifdef SNK_PHASE_TIMING  // experiment build (tools/phase_rows.py)
+  long long tA = 0, tB = 0, tC = 0, tD = 0; const long long tStart = clock64();
+#endif
   // Software pipeline over envs: warp 0 (producer) steps env e_next and builds its code grid while
   // warps 1..4 (consumers) expand and stream out the image of env e from the other grid.
   long long e = blockIdx.x;
@@ -572,7 +655,13 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
         const long long en = rep == 0 ? eb : eb + gridDim.x;
         u8* code = codes + ((it == 0 ? rep : it + 1) & 1) * code_stride;
         if (en >= p.N) continue;
+#ifdef SNK_PHASE_TIMING
+        const long long ta0 = clock64();
+#endif
         advance_env<RULES>(p, en, lane, sc, bm, errs, st);
+#ifdef SNK_PHASE_TIMING
+        const long long ta1 = clock64(); tA += ta1 - ta0;
+#endif
         uint4* c16 = reinterpret_cast<uint4*>(code);
         for (int i = lane; i < code_stride / 16; i += 32) c16[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
@@ -600,6 +689,9 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
         }
         for (int i = lane; i < V; i += 32) { code[i] = 255; code[(V - 1) * V + i] = 255; code[i * V] = 255; code[i * V + V - 1] = 255; }
         __syncwarp();
+#ifdef SNK_PHASE_TIMING
+        tB += clock64() - ta1;
+#endif
       }
     }
     if (it == 0) __syncthreads();  // grid 0 ready
@@ -609,39 +701,24 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
       const u8* code = codes + (it & 1) * code_stride;
       const u8* fgrid = RULES == SNK_RULES_CLASSIC ? nullptr : p.grid + e * p.grid_stride;
       u8* out = p.obs + e * (long long)p.E;
+#ifdef SNK_PHASE_TIMING
+      const long long tc0 = clock64();
+#endif
       for (int c = 0; c < n_chunks; ++c) {
         u8* tile = tiles + (issued & 1) * p.tile_stride;
+#ifdef SNK_PHASE_TIMING
+        const long long tw0 = clock64();
+#endif
         if (issued >= 2) {  // the copy that last used this buffer has been read by the engine
           if (ct == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           consumer_sync(cn);
         }
+#ifdef SNK_PHASE_TIMING
+        tD += clock64() - tw0;
+#endif
         const int r0 = c * R, rows = min(R, V - r0), cells = rows * V;
-        for (int i = ct; i < cells; i += cn) {
-          int cd = code[r0 * V + i];
-          if (RULES != SNK_RULES_CLASSIC && cd == 0 && fgrid[r0 * V + i]) cd = 1;  // fruit: lowest paint priority
-          u32 rgb = 0;
-          int self = -1;
-          if (cd == 1) rgb = 255u;
-          else if (cd == 255) rgb = 0xffffffu;
-          else if (cd >= 3) { self = (cd - 3) >> 1; rgb = snake_rgb(false, (cd - 3) & 1); }
-          u32 w0, w1, w2;
-          pattern3(rgb, w0, w1, w2);
-          u8* px = tile + i * C;
-          if ((C & 15) == 0) {
-            uint4* q = reinterpret_cast<uint4*>(px);
-            for (int j = 0; j < C / 16; ++j) {  // word index 4j: period 3 words
-              const int ph = (4 * j) % 3;
-              const u32 a0 = ph == 0 ? w0 : ph == 1 ? w1 : w2, a1 = ph == 0 ? w1 : ph == 1 ? w2 : w0, a2 = ph == 0 ? w2 : ph == 1 ? w0 : w1;
-              q[j] = make_uint4(a0, a1, a2, a0);
-            }
-          } else {
-            for (int j = 0; j < C; ++j) px[j] = (u8)(rgb >> (8 * (j % 3)));
-          }
-          if (self >= 0 && self < K) {
-            const u32 own = snake_rgb(true, (cd - 3) & 1);
-            px[3 * self] = (u8)own; px[3 * self + 1] = (u8)(own >> 8); px[3 * self + 2] = (u8)(own >> 16);
-          }
-        }
+        if (C == 48) rows_expand<RULES, 48>(code + r0 * V, fgrid ? fgrid + r0 * V : nullptr, tile, cells, C, K, ct, cn);
+        else rows_expand<RULES, 0>(code + r0 * V, fgrid ? fgrid + r0 * V : nullptr, tile, cells, C, K, ct, cn);
         fence_async_smem();
         consumer_sync(cn);
         if (ct == 0) {
@@ -652,10 +729,18 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
         }
         ++issued;
       }
+#ifdef SNK_PHASE_TIMING
+      tC += clock64() - tc0;
+#endif
     }
     __syncthreads();  // grid (it + 1) & 1 built, grid it & 1 consumed
   }
   if (tid == 32) bulk_wait_all();
+#ifdef SNK_PHASE_TIMING  // total, producer logic, producer grid build, consumers, of which TMA read-wait
+  if (tid == 0) { atomicAdd(&p.stats[3], (double)(clock64() - tStart)); atomicAdd(&p.stats[4], (double)tA); atomicAdd(&p.stats[5], (double)tB); }
+  if (tid == 32) { atomicAdd(&p.stats[6], (double)tC); atomicAdd(&p.stats[7], (double)tD); }
+  st.len_sum = st.fruits = st.deaths = st.cells = st.draws = 0.f;
+#endif
   if (warp == 0) flush_stats(p, st, errs, s_stats, lane);
   __syncthreads();
   if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);

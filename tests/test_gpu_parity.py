@@ -234,6 +234,22 @@ def test_tile_kernel_golden_replay(sb, monkeypatch):
     monkeypatch.delenv("SNK_FORCE_KERNEL")
 
 
+@pytest.mark.parametrize("rules,S,D", [("adversarial", 32, 40), ("cut", 16, 24)])
+def test_large_field_many_views(sb, monkeypatch, rules, S, D):
+    """The large-field kernel with 32 views (96-byte pixels, the maximum snake count) and with 16 views on a small board."""
+    monkeypatch.setenv("SNK_FORCE_KERNEL", "rows")
+    N = 24
+    kw = dict(size=D, n_snakes=S, rules=rules, seed=5)
+    env = sb.SnakeVecEnv(N, **kw)
+    assert env.launch_info()["kernel"] == "k_step_rows"
+    co = c_oracle.COracle(N, **kw)
+    assert np.array_equal(env.reset().cpu().numpy(), co.reset())
+    for t in range(40):
+        a = c_oracle.gen_actions(co.cfg, t, 5, env.action_space.n)
+        _compare_step(env, co, a, "%dx%d %s step %d" % (D, D, rules, t), check_state=(t % 10 == 0))
+    env.close()
+
+
 @pytest.mark.parametrize("rules", ["classic", "cut"])
 def test_large_field_16_snakes_64x64(sb, rules):
     """BASELINE configs[4] geometry (16 snakes, 64x64, 209 KB of observation per env)."""

@@ -13,6 +13,7 @@ nvcc $F -DSNK_TU=1 -DLANE_COMBOS_OVERRIDE -c -o variants/_o_$name/k1.o $C/snk_ke
 nvcc $F -DSNK_TU=2 -DLANE_COMBOS_OVERRIDE -c -o variants/_o_$name/k2.o $C/snk_kernels.cu &
 nvcc $F -DSNK_TU=3 -DLANE_COMBOS_OVERRIDE -c -o variants/_o_$name/k3.o $C/snk_kernels.cu &
 wait
+for o in api k0 k1 k2 k3; do [ -f variants/_o_$name/$o.o ] || { echo "FAILED: $o did not compile"; rm -rf variants/_o_$name; exit 1; }; done
 nvcc --shared -gencode arch=compute_100a,code=sm_100a -o variants/libsnk_$name.so variants/_o_$name/*.o
 rm -rf variants/_o_$name
 echo built variants/libsnk_$name.so

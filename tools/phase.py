@@ -1,4 +1,4 @@
-"""Per-phase warp cycles of k_step_lane (SNK_LIB = a -DSNK_PHASE_TIMING build): logic / paint / store+wait / un-paint."""
+"""Per-phase warp cycles of k_step_lane (tools/build_variant.sh phase -DSNK_PHASE_TIMING; SNK_LIB=variants/libsnk_phase.so): logic / paint / store+wait / un-paint."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, snakes_b200
