@@ -673,19 +673,27 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
         // codes grow in paint order, so "later overwrites earlier" is a per-cell max: all snakes at
         // once, repeated until no lane had to raise a cell (cells shared by two snakes are rare)
         const u16* rings = p.body + en * S * cap;
-        for (int pass = 0; pass < 64; ++pass) {
-          int changed = 0;
-          for (int s = 0; s < S; ++s) {
-            const u32 a = sc[REC_SNAKE0 + 2 * s];
-            const int len = a >> 16, hs = a & 0xffff;
-            for (int i = lane; i < len; i += 32) {
-              const int cell = ring_at(rings + s * cap, hs, i, cap);
-              const u8 mine = (u8)(3 + 2 * s + (i == 0));
-              if (code[cell] < mine) { code[cell] = mine; changed = 1; }
+        {
+          // all snakes' segments as one list, 32 per pass (seg_scan / seg_locate, snk_device.cuh): the ring
+          // reads of a pass are independent loads
+          const u32 a_mine = lane < S ? sc[REC_SNAKE0 + 2 * lane] : 0u;
+          const int len_mine = a_mine >> 16;
+          const SegScan sg = seg_scan(len_mine, lane);
+          for (int pass = 0; pass < 64; ++pass) {
+            int changed = 0;
+            for (int t0 = 0; t0 < sg.total; t0 += 32) {
+              int j, i;
+              const bool have = seg_locate(sg, len_mine, S, t0 + lane, j, i);
+              const int hs = __shfl_sync(FULL, (int)(a_mine & 0xffff), j);
+              if (have) {
+                const int cell = ring_at(rings + j * cap, hs, i, cap);
+                const u8 mine = (u8)(3 + 2 * j + (i == 0));
+                if (code[cell] < mine) { code[cell] = mine; changed = 1; }
+              }
             }
+            __syncwarp();
+            if (!__any_sync(FULL, changed)) break;
           }
-          __syncwarp();
-          if (!__any_sync(FULL, changed)) break;
         }
         for (int i = lane; i < V; i += 32) { code[i] = 255; code[(V - 1) * V + i] = 255; code[i * V] = 255; code[i * V + V - 1] = 255; }
         __syncwarp();
