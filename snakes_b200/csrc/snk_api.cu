@@ -174,9 +174,9 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   int R = 0;
   if (p.E % 16 == 0) {
     const int unit = 16 / gcd(V * p.C, 16);
-    // chunk size and CTA shape measured on B200 at 16 snakes on 64x64, 16 384 envs: 4 warps (1 producer + 3 consumers)
-    // give 7 CTAs per SM; classic: 8 KB chunks 799 us (160 threads, 12 KB: 831 us); count-grid rules: 12 KB 1022 us (1136 us)
-    { const char* rk = getenv("SNK_ROWS_KB"); const size_t lim = (size_t)(rk ? atoi(rk) : cfg->rules == SNK_RULES_CLASSIC ? 8 : 12) * 1024;
+    // chunk size and CTA shape measured on B200 at 16 snakes on 64x64: 4 warps (1 producer + 3 consumers) give 7 CTAs
+    // per SM, and 8 KB chunks beat 12 KB (32 768 envs: classic 1280 us, cut 1502 vs 1551 us)
+    { const char* rk = getenv("SNK_ROWS_KB"); const size_t lim = (size_t)(rk ? atoi(rk) : 8) * 1024;
       for (int r = unit; r <= V && ((size_t)r * V * p.C <= lim || !R); r += unit) { if ((size_t)r * V * p.C > 48 * 1024) break; R = r; } }
   }
   plan.kind = TE ? KIND_LANE : smem_tile <= 110 * 1024 ? KIND_TILE : R ? KIND_ROWS : KIND_DENSE;

@@ -601,26 +601,9 @@ __device__ __forceinline__ void rows_emit(u8* __restrict__ tile, int i, int cd, 
 }
 
 // Expand the `cells` cell codes of one chunk, one thread per cell.
-template <int RULES, int CT>
-__device__ __forceinline__ void rows_expand(const u8* __restrict__ code, const u8* __restrict__ fgrid, u8* __restrict__ tile,
-                                            int cells, int C, int K, int ct, int cn) {
-  if (RULES == SNK_RULES_CLASSIC) {
-    for (int i = ct; i < cells; i += cn) rows_emit<CT>(tile, i, code[i], C, K);
-  } else {
-    // count-grid rules: the fruit counts of four cells are fetched from HBM / L2 before any of them is
-    // expanded (one memory round trip per four cells instead of one per cell)
-    for (int i0 = ct; i0 < cells; i0 += 4 * cn) {
-      int cdv[4];
-      u8 fv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { const int i = i0 + k * cn; cdv[k] = i < cells ? (int)code[i] : -1; }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) fv[k] = cdv[k] == 0 ? fgrid[i0 + k * cn] : (u8)0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (cdv[k] >= 0) rows_emit<CT>(tile, i0 + k * cn, fv[k] ? 1 : cdv[k], C, K);  // fruit: lowest paint priority
-    }
-  }
+template <int CT>
+__device__ __forceinline__ void rows_expand(const u8* __restrict__ code, u8* __restrict__ tile, int cells, int C, int K, int ct, int cn) {
+  for (int i = ct; i < cells; i += cn) rows_emit<CT>(tile, i, code[i], C, K);
 }
 
 template <int RULES>
@@ -668,7 +651,22 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
         if (RULES == SNK_RULES_CLASSIC) {
           const u16* fr = reinterpret_cast<const u16*>(sc + REC_SNAKE0 + 2 * S);
           if (lane < F) code[fr[lane]] = 1;
-        }  // count-grid rules: the consumers read the fruit grid themselves (it is stable while env `en` is output)
+        } else {
+          // count-grid rules: cells holding fruit get code 1 here, read with independent 16-byte loads (the
+          // grid was last written by this warp); snakes and the border overwrite it below
+          const uint4* g16 = reinterpret_cast<const uint4*>(p.grid + en * p.grid_stride);
+          const int n16 = p.grid_stride / 16;
+#pragma unroll 3
+          for (int i = lane; i < n16; i += 32) {
+            const uint4 v = g16[i];
+            if (v.x | v.y | v.z | v.w) {
+              const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                if (((w[k >> 2] >> (8 * (k & 3))) & 0xffu) && 16 * i + k < VV) code[16 * i + k] = 1;
+            }
+          }
+        }
         __syncwarp();
         // codes grow in paint order, so "later overwrites earlier" is a per-cell max: all snakes at
         // once, repeated until no lane had to raise a cell (cells shared by two snakes are rare)
@@ -707,7 +705,6 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
     if (warp > 0) {
       const int ct = tid - 32, cn = blockDim.x - 32;
       const u8* code = codes + (it & 1) * code_stride;
-      const u8* fgrid = RULES == SNK_RULES_CLASSIC ? nullptr : p.grid + e * p.grid_stride;
       u8* out = p.obs + e * (long long)p.E;
 #ifdef SNK_PHASE_TIMING
       const long long tc0 = clock64();
@@ -725,8 +722,8 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
         tD += clock64() - tw0;
 #endif
         const int r0 = c * R, rows = min(R, V - r0), cells = rows * V;
-        if (C == 48) rows_expand<RULES, 48>(code + r0 * V, fgrid ? fgrid + r0 * V : nullptr, tile, cells, C, K, ct, cn);
-        else rows_expand<RULES, 0>(code + r0 * V, fgrid ? fgrid + r0 * V : nullptr, tile, cells, C, K, ct, cn);
+        if (C == 48) rows_expand<48>(code + r0 * V, tile, cells, C, K, ct, cn);
+        else rows_expand<0>(code + r0 * V, tile, cells, C, K, ct, cn);
         fence_async_smem();
         consumer_sync(cn);
         if (ct == 0) {
