@@ -641,6 +641,19 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
 #ifdef SNK_PHASE_TIMING
         const long long ta0 = clock64();
 #endif
+        {
+          // L2 prefetch: the fruit count grid of this env (read at the end of the build, after the whole step)
+          // and the record + actions of the env this warp steps next (a whole env period ahead)
+          if (RULES != SNK_RULES_CLASSIC) {
+            const u8* g = p.grid + en * p.grid_stride;
+            for (int off = lane * 128; off < p.grid_stride; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + off));
+          }
+          const long long nx = en + gridDim.x;
+          if (nx < p.N) {
+            if (lane < (p.RW * 4 + 127) / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const u8*>(p.rec + nx * p.RW) + lane * 128));
+            if (lane == 31 && p.actions) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + nx * S));
+          }
+        }
         advance_env<RULES>(p, en, lane, sc, bm, errs, st);
 #ifdef SNK_PHASE_TIMING
         const long long ta1 = clock64(); tA += ta1 - ta0;
