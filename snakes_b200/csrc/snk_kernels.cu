@@ -190,18 +190,21 @@ __global__ void __launch_bounds__(BLOCK) k_step_tile(const Params p) {
 // Stream one painted image (TE envs, 16-byte aligned in HBM) out of shared memory: one TMA bulk
 // copy issued by lane 0 (which then waits until the engine has READ the image, so it may be
 // modified), or LDS.128 + STG.128 by all lanes; the last, partial image uses plain byte stores.
+#ifndef SNK_LANE_BULK
+#define SNK_LANE_BULK 16384  // bytes per bulk copy of the lane kernel's image store
+#endif
 __device__ __forceinline__ void store_image(const Params& p, const u8* tile, int tile_bytes, long long e0, int lane) {
   const long long left = p.N - e0;
   u8* gdst = p.obs + e0 * (long long)p.E;
   if (left >= p.TE && p.store_mode == 0) {
     if (lane == 0) {
       if (!p.obs_evict_first) {
-        for (int off = 0; off < tile_bytes; off += 16384)
-          bulk_store_s2g(gdst + off, tile + off, (u32)min(16384, tile_bytes - off));
+        for (int off = 0; off < tile_bytes; off += SNK_LANE_BULK)
+          bulk_store_s2g(gdst + off, tile + off, (u32)min(SNK_LANE_BULK, tile_bytes - off));
       } else {
         const u64 pol = l2_evict_first_policy();
-        for (int off = 0; off < tile_bytes; off += 16384)
-          bulk_store_s2g_hint(gdst + off, tile + off, (u32)min(16384, tile_bytes - off), pol);
+        for (int off = 0; off < tile_bytes; off += SNK_LANE_BULK)
+          bulk_store_s2g_hint(gdst + off, tile + off, (u32)min(SNK_LANE_BULK, tile_bytes - off), pol);
       }
       bulk_commit();
       bulk_wait_read();
