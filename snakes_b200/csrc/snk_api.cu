@@ -208,6 +208,7 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     plan.ws = plan.kind == KIND_LANE && (lv ? !strcmp(lv, "ws") : (p.E < 2048 && (N + 31) / 32 >= 2LL * h->n_sm));
     plan.split = plan.kind == KIND_LANE && lv && !strcmp(lv, "split");
     { const char* pd = getenv("SNK_PDL"); plan.pdl = !(pd && !strcmp(pd, "0")); }
+
     const char* lw = getenv("SNK_LOGIC_WARPS");
     p.PW = 2;
     logic_warps = lw ? atoi(lw) : 3;
@@ -218,6 +219,18 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     p.RW = (REC_SNAKE0 + 2 * S + 2 + 3) & ~3;
     p.TE = TE; p.W = 32;
     p.tile_stride = (int)(((size_t)TE * p.E + 127) & ~(size_t)127);
+    {  // un-paint by zero-fill + border redraw (lane_restore) once a lane would walk more than restore_thr segments:
+       // the restore costs one 16-byte store per 512 bytes of image plus the border units of one env spread over its
+       // LPE lanes; a walked segment costs about 16 instructions.  Measured on B200 (2x19x19, 131072 envs, fruit-seeking
+       // policy, sum of lengths 22): thresholds 3 / 5 / 8 / 12 -> 145.9 / 145.1 / 146.8 / 152.9 us, always-walk 161.1 us;
+       // random actions (sum of lengths 4.4) unchanged.  SNK_RESTORE_THR overrides (0 = always walk).
+      const int U = (p.C & 1) ? 1 : 2, LPE = 32 / TE;
+      const int border_units = (2 * (V * p.C + p.C) + (V - 3) * 2 * p.C) / U;
+      const int stores = (int)((size_t)TE * p.E / 512) + border_units / LPE;
+      p.restore_thr = stores / 16 < 3 ? 3 : stores / 16;
+      const char* rt = getenv("SNK_RESTORE_THR");
+      if (rt) p.restore_thr = atoi(rt);
+    }
     plan.block = plan.ws ? 32 * (p.PW + logic_warps) : 64;
     plan.smem = (size_t)2 * p.tile_stride;
     p.n_groups = (N + 31) / 32;

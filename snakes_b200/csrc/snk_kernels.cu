@@ -253,25 +253,32 @@ __device__ __forceinline__ void reduce_lane_stats(const Params& p, LaneStats st,
 template <int S, int RULES>
 __global__ void __launch_bounds__(128) k_lane_logic(const Params p) {
   __shared__ double s_stats[SNK_NSTATS];
+  __shared__ u32 s_bm[4][SPAWN_WORDS];  // per warp: scratch of group_spawn
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
   __syncthreads();
   LaneStats st = {0, 0, 0, 0, 0, 0, 0, 0};
   u32 errs = 0;
   const long long e = (long long)blockIdx.x * blockDim.x + tid;
-  if (e < p.N) {
+  {
+    const bool valid = e < p.N;
     LaneEnv<S> env;
+#pragma unroll
+    for (int s = 0; s < S; ++s) { env.head[s] = 0; env.len[s] = 0; env.c0[s] = 0; env.grow[s] = 0; env.vel[s] = 0; }
+    env.fruit[0] = env.fruit[1] = env.fruit[2] = env.fruit[3] = 0;
+    env.spare = 0;
     LaneRng rng;
     rng.have = false; rng.blk = 0;
     const FruitSet grid = fruit_set(p, e);
-    const LaneRaw<S> raw = lane_fetch<S>(p, e, p.mode == MODE_STEP);
-    lane_unpack<S>(raw, env);
+    LaneRaw<S> raw;
+    raw.act = 0;
+    if (valid) { raw = lane_fetch<S>(p, e, p.mode == MODE_STEP); lane_unpack<S>(raw, env); }
     if (p.mode == MODE_STEP) {
-      lane_step<S, RULES>(p, e, env, raw.act, rng, grid, errs, st);
-    } else if (!p.mask || p.mask[e]) {
+      lane_step<S, RULES>(p, e, valid, env, raw.act, rng, grid, s_bm[tid >> 5], errs, st);
+    } else if (valid && (!p.mask || p.mask[e])) {
       lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);
     }
-    lane_store<S>(p, e, env);
+    if (valid) lane_store<S>(p, e, env);
   }
   reduce_lane_stats(p, st, errs, s_stats, lane);
   __syncthreads();
@@ -301,12 +308,13 @@ __global__ void __launch_bounds__(64) k_lane_paint(const Params p) {
     const long long next = item + stride;
     const PaintEnv<S> nxt = paint_env_from_memory<S>(p, next < n_items ? next * TE + slot : p.N);
     const long long e0 = item * TE;
+    const bool restore = lane_wants_restore<S>(p, cur.len, LPE);
     lane_paint<S, RULES, K, true>(p, cur, e0 + slot, sub, LPE, img);
     fence_async_smem();
     __syncwarp();
     store_image(p, tile, tile_bytes, e0, lane);
     __syncwarp();
-    lane_paint<S, RULES, K, false>(p, cur, e0 + slot, sub, LPE, img);
+    lane_unpaint<S, RULES, K>(p, cur, e0 + slot, sub, LPE, tile, tile_bytes, img, lane, restore);
     __syncwarp();
     cur = nxt;
     item = next;
@@ -326,6 +334,7 @@ __global__ void __launch_bounds__(160, 5) k_step_lane_ws(const Params p) {
   extern __shared__ __align__(128) u8 smem[];
   __shared__ double s_stats[SNK_NSTATS];
   __shared__ int s_ready[8];
+  __shared__ u32 s_bm[5][SPAWN_WORDS];  // per warp: scratch of group_spawn (logic warps)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int PW = p.PW, LW = (blockDim.x >> 5) - PW;
   const int TE = p.TE, LPE = 32 / TE, E = p.E, IPB = 32 / TE;  // images per 32-env batch
@@ -354,12 +363,13 @@ __global__ void __launch_bounds__(160, 5) k_step_lane_ws(const Params p) {
         while (ready[l] <= r) __nanosleep(64);
         __threadfence_block();
         const PaintEnv<S> pe = paint_env_from_memory<S>(p, e0 + slot);
+        const bool restore = lane_wants_restore<S>(p, pe.len, LPE);
         lane_paint<S, RULES, K, true>(p, pe, e0 + slot, sub, LPE, img);
         fence_async_smem();
         __syncwarp();
         store_image(p, tile, tile_bytes, e0, lane);
         __syncwarp();
-        lane_paint<S, RULES, K, false>(p, pe, e0 + slot, sub, LPE, img);
+        lane_unpaint<S, RULES, K>(p, pe, e0 + slot, sub, LPE, tile, tile_bytes, img, lane, restore);
         __syncwarp();
       }
     }
@@ -371,19 +381,25 @@ __global__ void __launch_bounds__(160, 5) k_step_lane_ws(const Params p) {
       const long long base_b = ((long long)r * gridDim.x + blockIdx.x) * LW;
       if (base_b >= n_batches) break;
       const long long e = (base_b + lw) * 32 + lane;
-      if (e < p.N && p.mode != MODE_OBSERVE) {
+      if (p.mode != MODE_OBSERVE) {
+        const bool valid = e < p.N;
         LaneEnv<S> env;
+#pragma unroll
+        for (int s = 0; s < S; ++s) { env.head[s] = 0; env.len[s] = 0; env.c0[s] = 0; env.grow[s] = 0; env.vel[s] = 0; }
+        env.fruit[0] = env.fruit[1] = env.fruit[2] = env.fruit[3] = 0;
+        env.spare = 0;
         LaneRng rng;
         rng.have = false; rng.blk = 0;
         const FruitSet grid = fruit_set(p, e);
-        const LaneRaw<S> raw = lane_fetch<S>(p, e, p.mode == MODE_STEP);
-        lane_unpack<S>(raw, env);
+        LaneRaw<S> raw;
+        raw.act = 0;
+        if (valid) { raw = lane_fetch<S>(p, e, p.mode == MODE_STEP); lane_unpack<S>(raw, env); }
         if (p.mode == MODE_STEP) {
-          lane_step<S, RULES>(p, e, env, raw.act, rng, grid, errs, st);
-        } else if (!p.mask || p.mask[e]) {
+          lane_step<S, RULES>(p, e, valid, env, raw.act, rng, grid, s_bm[warp], errs, st);
+        } else if (valid && (!p.mask || p.mask[e])) {
           lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);
         }
-        lane_store<S>(p, e, env);
+        if (valid) lane_store<S>(p, e, env);
       }
       __threadfence_block();  // records / chain words / fruit grid before the round counter
       __syncwarp();
@@ -403,6 +419,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   extern __shared__ __align__(128) u8 smem[];
   __shared__ double s_stats[SNK_NSTATS];
   __shared__ __align__(8) u64 s_bar[2];
+  __shared__ u32 s_bm[2][SPAWN_WORDS];  // per warp: scratch of group_spawn
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
   const int TE = p.TE, LPE = 32 / TE, E = p.E;
   const int tile_bytes = TE * E;
@@ -416,6 +433,9 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
   __syncthreads();
   LaneStats st = {0, 0, 0, 0, 0, 0, 0, 0};
+#ifdef SNK_PHASE_LOGIC
+  st.ph[0] = st.ph[1] = st.ph[2] = st.ph[3] = 0;
+#endif
   u32 errs = 0;
   const int slot = lane / LPE, sub = lane - slot * LPE;
   u8* img = tile + slot * E;
@@ -443,20 +463,22 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
 #pragma unroll
     for (int s = 0; s < S; ++s) { env.head[s] = 0; env.len[s] = 0; env.c0[s] = 0; env.grow[s] = 0; env.vel[s] = 0; }
     env.fruit[0] = env.fruit[1] = env.fruit[2] = env.fruit[3] = 0;
-    if (valid) {
+    env.spare = 0;
+    {
       LaneRng rng;
       rng.have = false; rng.blk = 0;
       const FruitSet grid = fruit_set(p, e);
-      lane_unpack<S>(raw, env);
+      if (valid) lane_unpack<S>(raw, env);
       if (stepping) {
-        lane_step<S, RULES>(p, e, env, raw.act, rng, grid, errs, st);
-      } else if (p.mode == MODE_RESET) {
+        lane_step<S, RULES>(p, e, valid, env, raw.act, rng, grid, s_bm[warp], errs, st);
+      } else if (valid && p.mode == MODE_RESET) {
         if (!p.mask || p.mask[e]) lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);
       }
-      if (p.mode != MODE_OBSERVE) lane_store<S>(p, e, env);
+      if (valid && p.mode != MODE_OBSERVE) lane_store<S>(p, e, env);
     }
     // records + actions of this warp's NEXT batch: in flight while the current one is painted
     if (b + stride < n_batches && (b + stride) * 32 + lane < p.N) raw = lane_fetch<S>(p, (b + stride) * 32 + lane, stepping);
+    const bool restore = lane_wants_restore<S>(p, env.len, LPE);  // one decision for the batch's 32/TE images
     if (!have_image) { mbar_wait(&s_bar[warp], 0); have_image = true; }
     __syncwarp();  // chain words / fruit grid written by the owner lane are read by the painting lanes
 #ifdef SNK_PHASE_TIMING
@@ -477,7 +499,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
 #ifdef SNK_PHASE_TIMING
       { const long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
 #endif
-      lane_paint<S, RULES, K, false>(p, pe, e0 + slot, sub, LPE, img);
+      lane_unpaint<S, RULES, K>(p, pe, e0 + slot, sub, LPE, tile, tile_bytes, img, lane, restore);
       __syncwarp();
 #ifdef SNK_PHASE_TIMING
       { const long long t1 = clock64(); tD += t1 - t0; t0 = t1; }
@@ -489,6 +511,12 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
     atomicAdd(&p.stats[3], (double)(clock64() - tStart)); atomicAdd(&p.stats[4], (double)tA); atomicAdd(&p.stats[5], (double)tB);
     atomicAdd(&p.stats[6], (double)tC); atomicAdd(&p.stats[7], (double)tD);
   }
+#ifdef SNK_PHASE_LOGIC  // the four slots carry move+push / respawns / death test / tail+reset of the logic instead
+  if (lane == 0) {
+    atomicAdd(&p.stats[4], (double)(st.ph[0] - tA)); atomicAdd(&p.stats[5], (double)(st.ph[1] - tB));
+    atomicAdd(&p.stats[6], (double)(st.ph[2] - tC)); atomicAdd(&p.stats[7], (double)(st.ph[3] - tD));
+  }
+#endif
   st.len_sum = st.fruits = st.deaths = st.cells = st.draws = 0.f;
 #endif
   if (!have_image) mbar_wait(&s_bar[warp], 0);  // never leave with a bulk copy into our shared memory in flight

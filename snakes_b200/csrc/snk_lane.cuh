@@ -61,55 +61,176 @@ __device__ __forceinline__ void chain_walk(int head, int len, u32 c0, const u32*
   }
 }
 
+// the raw Philox word of draw index env.ctr (no side effect but the one-block cache)
 template <int S>
-__device__ __forceinline__ u32 lane_draw(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, u32 n, u32& errs, float& draws) {
-  const u32 idx = env.ctr++;
-  draws += 1.f;
-  if (p.rng_mode == SNK_RNG_TAPE) {
-    const u64 pos = p.tape_off[e] + idx;
-    if (pos >= p.tape_off[e + 1]) { errs |= SNK_DEVERR_TAPE_UNDERRUN; return 0; }
-    if (p.tape_bounds && p.tape_bounds[pos] != n) errs |= SNK_DEVERR_TAPE_BOUND;
-    return p.tape_vals[pos];
-  }
-  const u32 blk = idx >> 2;
+__device__ __forceinline__ u32 lane_philox_peek(const Params& p, long long e, const LaneEnv<S>& env, LaneRng& rng) {
+  const u32 idx = env.ctr, blk = idx >> 2;
   if (!rng.have || rng.blk != blk) {
     rng.o = philox_block(blk, 0, 0, (u32)(p.seed >> 32), (u32)p.seed, (u32)(p.env_id_base + e));
     rng.blk = blk; rng.have = true;
   }
   const u32 sel = idx & 3;
-  const u32 x = sel == 0 ? rng.o.w[0] : sel == 1 ? rng.o.w[1] : sel == 2 ? rng.o.w[2] : rng.o.w[3];
+  return sel == 0 ? rng.o.w[0] : sel == 1 ? rng.o.w[1] : sel == 2 ? rng.o.w[2] : rng.o.w[3];
+}
+
+template <int S>
+__device__ __forceinline__ u32 lane_draw(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, u32 n, u32& errs, float& draws) {
+  draws += 1.f;
+  if (p.rng_mode == SNK_RNG_TAPE) {
+    const u32 idx = env.ctr++;
+    const u64 pos = p.tape_off[e] + idx;
+    if (pos >= p.tape_off[e + 1]) { errs |= SNK_DEVERR_TAPE_UNDERRUN; return 0; }
+    if (p.tape_bounds && p.tape_bounds[pos] != n) errs |= SNK_DEVERR_TAPE_BOUND;
+    return p.tape_vals[pos];
+  }
+  const u32 x = lane_philox_peek<S>(p, e, env, rng);
+  env.ctr++;
   return __umulhi(x, n);
 }
 
-// safe_choose_cell (:202-217), one lane: bitmap of the y-major indices of every live body cell
-// (un-bounds-checked: cellinfo carries the aliased index of an out-of-board head), k-th free one.
+// Position of segment i without walking: the 2-bit codes before it are counted per direction with
+// popcounts, pid_i = head - V*(#(+V) - #(-V)) - (#(+1) - #(-1)).
+template <bool AT_L2 = false>  // AT_L2: the chain words were written by another lane a moment ago -- read them at the L2
+__device__ __forceinline__ int chain_pos(int head, u32 c0, const u32* __restrict__ ch, int V, int i) {
+  int nV = 0, n1 = 0;
+  u32 w = c0;
+  int k = 0;
+  for (; i - 16 * k > 16; ++k) {  // whole words before the one holding code i-1 (bodies longer than 17)
+    const u32 lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+    nV += 16 - __popc(lo | hi) - __popc(hi & ~lo);
+    n1 += __popc(lo & ~hi) - __popc(lo & hi);
+    w = AT_L2 ? __ldcg(ch + k + 1) : ch[k + 1];
+  }
+  const int r = i - 16 * k;  // 0..16 codes of word k
+  const u32 m = r >= 16 ? 0x55555555u : ((1u << (2 * r)) - 1u) & 0x55555555u;
+  const u32 lo = w & m, hi = (w >> 1) & m;
+  nV += r - __popc(lo | hi) - __popc(hi & ~lo);
+  n1 += __popc(lo & ~hi) - __popc(lo & hi);
+  return head - V * nV - n1;
+}
+
+// safe_choose_cell (:202-217), warp-cooperative.  Under a policy that eats, about six lanes of every warp respawn a
+// fruit on every step; a one-lane form (a serial walk of all bodies with a bitmap in local memory, about 5 k cycles;
+// the first version of this kernel) then sits on the warp's critical path.  Here the warp serves up to FOUR envs
+// ("owners", the lowest set bits of `mm`) per pass, eight lanes each: lane `sub` of a group takes segments sub,
+// sub+8, ... of each body of its owner (chain_pos is O(1)) and ORs their y-major bits (cellinfo: the reference's
+// un-bounds-checked aliasing of an out-of-board head) into the group's 32 words of shared memory; each lane then
+// counts the free cells of four words, a 3-step shuffle scan gives the total, the owner turns its Philox word
+// (`raw`, fetched by all owners at once before the pass) or its tape value into k, and the lane whose words hold the
+// k-th free cell looks it up.  Same draws, same cell as the reference.  ALL 32 lanes must call it; `bm` = SPAWN_WORDS
+// words of shared memory private to the warp.  Returns true in the lanes that were served, with their cell.
+// The two phases are real function calls (one copy per kernel instead of one per snake: with the walks inlined S times
+// the kernel outgrew the instruction cache -- 9 000 instructions ran the headline 12 % slower than 6 900), so they
+// take values, not references: a reference to the env or to Params would force those into local memory.
+#define SPAWN_WORDS 136  // 4 groups x 32 bitmap words, 4 totals, 4 cells
 template <int S>
-__device__ __forceinline__ int lane_spawn(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, u32& errs, float& draws) {
-  u32 bm[32];
-  const int nW = p.bm_words, DD = p.D * p.D;
-  for (int w = 0; w < nW; ++w) bm[w] = 0;
+struct SpawnBodies {  // the bodies of one env as the lane that owns it holds them
+  long long e;
+  int head[S], len[S];
+  u32 c0[S];
+};
+
+// phase 1: bitmaps of the (up to four) owners of this pass; returns the number of free cells to the served owners
+template <int S>
+__device__ __noinline__ u32 spawn_totals(SpawnBodies<S> me, u32 mm, u32* bm, const u32* chain, int CW, int V, const u32* cellinfo, int nW, int DD) {
+  const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
+  u32 m = mm;
+  for (int t = 0; t < g; ++t) m &= m - 1;
+  const bool active = m != 0;                      // my group serves the (g+1)-th owner
+  const int src = active ? __ffs(m) - 1 : lane;
+  const long long eo = __shfl_sync(FULL, me.e, src);
+  u32* b = bm + g * 32;
+  b[sub] = 0; b[sub + 8] = 0; b[sub + 16] = 0; b[sub + 24] = 0;
+  __syncwarp();  // also orders the owners' chain-word stores before the other lanes' loads
 #pragma unroll
   for (int s = 0; s < S; ++s) {
-    chain_walk(env.head[s], env.len[s], env.c0[s], p.chain + (e * S + s) * p.CW, p.V, [&](int, int pid) {
-      const u32 idx = __ldg(p.cellinfo + pid) & 0x7fffffffu;
-      if (idx < (u32)DD) bm[idx >> 5] |= 1u << (idx & 31);
-    });
+    const int h = __shfl_sync(FULL, me.head[s], src);
+    int l = __shfl_sync(FULL, me.len[s], src);
+    if (!active) l = 0;
+    const u32 c0 = __shfl_sync(FULL, me.c0[s], src);
+    const u32* ch = chain + (eo * S + s) * CW;
+    for (int i = sub; i < l; i += 8) {
+      const u32 idx = __ldg(cellinfo + chain_pos(h, c0, ch, V, i)) & 0x7fffffffu;
+      if (idx < (u32)DD) atomicOr(&b[idx >> 5], 1u << (idx & 31));
+    }
   }
-  int total = 0;
-  for (int w = 0; w < nW; ++w) {
-    u32 fr = ~bm[w];
-    if (w == nW - 1 && (DD & 31)) fr &= (1u << (DD & 31)) - 1;
-    bm[w] = fr;
-    total += __popc(fr);
+  __syncwarp();
+  int c = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int w = 4 * sub + j;
+    u32 f = w < nW ? ~b[w] : 0u;
+    if (w == nW - 1 && (DD & 31)) f &= (1u << (DD & 31)) - 1;
+    b[w] = f;                                      // the words now hold the FREE cells (phase 2 reads them back)
+    c += __popc(f);
   }
-  if (total == 0) return p.V + 1;  // (0,0), no draw (:212-215)
-  int k = (int)lane_draw<S>(p, e, env, rng, (u32)total, errs, draws);
-  for (int w = 0; w < nW; ++w) {
-    const int c = __popc(bm[w]);
-    if (k < c) return p.idx2pid[w * 32 + (int)__fns(bm[w], 0, k + 1)];
-    k -= c;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, c, o, 8);
+    if (sub >= o) c += v;
   }
-  return p.V + 1;
+  if (sub == 7) bm[128 + g] = (u32)c;
+  __syncwarp();
+  const int rank = __popc(mm & ((1u << lane) - 1u));  // an owner's rank among the set bits = the group that served it
+  return (((mm >> lane) & 1u) && rank < 4) ? bm[128 + rank] : 0u;
+}
+
+// phase 2: k = the owner's draw (or -1); returns the k-th free cell (y-major order) to the served owners
+static __device__ __noinline__ int spawn_pick(int k, u32 mm, u32* bm, const u16* idx2pid) {
+  const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
+  u32 m = mm;
+  for (int t = 0; t < g; ++t) m &= m - 1;
+  const int src = m ? __ffs(m) - 1 : lane;
+  int kk = __shfl_sync(FULL, k, src);
+  if (!m) kk = -1;
+  const u32* b = bm + g * 32;
+  int c = 0;
+  u32 fr[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { fr[j] = b[4 * sub + j]; c += __popc(fr[j]); }
+  int incl = c;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, o, 8);
+    if (sub >= o) incl += v;
+  }
+  if (kk >= incl - c && kk < incl) {
+    int r = kk - (incl - c), idx = 0;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cj = __popc(fr[j]);
+      if (!found && r < cj) { idx = (4 * sub + j) * 32 + (int)__fns(fr[j], 0, r + 1); found = true; }
+      r -= cj;
+    }
+    bm[132 + g] = idx2pid[idx];
+  }
+  __syncwarp();
+  const int rank = __popc(mm & ((1u << lane) - 1u));
+  const int cell = (((mm >> lane) & 1u) && rank < 4) ? (int)bm[132 + rank] : 0;
+  __syncwarp();  // the next pass zeroes the words
+  return cell;
+}
+
+// one pass: returns true in the lanes that were served, with their cell
+template <int S>
+__device__ __forceinline__ bool group_spawn(const Params& p, long long e, LaneEnv<S>& env, LaneRng& rng, u32 raw, u32 mm, u32* bm, u32& errs,
+                                            float& draws, int& cell) {
+  const int lane = threadIdx.x & 31;
+  SpawnBodies<S> me;
+  me.e = e;
+#pragma unroll
+  for (int s = 0; s < S; ++s) { me.head[s] = env.head[s]; me.len[s] = env.len[s]; me.c0[s] = env.c0[s]; }
+  const u32 total = spawn_totals<S>(me, mm, bm, p.chain, p.CW, p.V, p.cellinfo, p.bm_words, p.D * p.D);
+  const bool served = ((mm >> lane) & 1u) && __popc(mm & ((1u << lane) - 1u)) < 4;
+  int k = -1;
+  if (served && total > 0) {
+    if (p.rng_mode == SNK_RNG_TAPE) k = (int)lane_draw<S>(p, e, env, rng, total, errs, draws);
+    else { env.ctr++; draws += 1.f; k = (int)__umulhi(raw, total); }
+  }
+  const int c = spawn_pick(k, mm, bm, p.idx2pid);
+  cell = k >= 0 ? c : p.V + 1;                     // (0,0), no draw, when nothing is free (:212-215)
+  return served;
 }
 
 
@@ -172,12 +293,24 @@ __device__ __forceinline__ void lane_reset(const Params& p, long long e, LaneEnv
 
 struct LaneStats {
   float steps, episodes, ret_sum, len_sum, fruits, deaths, cells, draws;
+#ifdef SNK_PHASE_LOGIC  // experiment build: warp cycles of the four parts of lane_step (move+push, respawns, death test, tail+reset)
+  long long ph[4];
+#endif
 };
+#ifdef SNK_PHASE_LOGIC
+#define SNK_LOGIC_MARK(k) { __syncwarp(__activemask()); const long long t_now = clock64(); st.ph[k] += t_now - t_mark; t_mark = t_now; }
+#define SNK_LOGIC_START long long t_mark; { __syncwarp(__activemask()); t_mark = clock64(); }
+#else
+#define SNK_LOGIC_MARK(k)
+#define SNK_LOGIC_START
+#endif
 
 // One env step in one lane (:166-197).
+// Called by ALL 32 lanes of the warp (the respawns are warp-cooperative); lanes without an env pass valid = false
+// and an env whose snakes all have length 0.  `bm` = SPAWN_WORDS words of shared memory private to the warp.
 template <int S, int RULES>
-__device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<S>& env, u32 act_packed, LaneRng& rng, const FruitSet& fs,
-                                          u32& errs, LaneStats& st) {
+__device__ __forceinline__ void lane_step(const Params& p, long long e, bool valid, LaneEnv<S>& env, u32 act_packed, LaneRng& rng, const FruitSet& fs,
+                                          u32* bm, u32& errs, LaneStats& st) {
   const int V = p.V, F = p.F;
   const u32* chain_e = p.chain + e * S * p.CW;
   int act[S];
@@ -185,57 +318,77 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<
   for (int s = 0; s < S; ++s) act[s] = (int)(int8_t)(act_packed >> (8 * s));
   u32 was_alive = 0, moved = 0, strike = 0;
   int eaten[S];
+  SNK_LOGIC_START
   // ---- update_snake for every snake in index order (:97-145)
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     eaten[s] = 0;
-    if (env.len[s] == 0) continue;
-    was_alive |= 1u << s;
-    const int a = act[s];
-    int vel = env.vel[s];
-    if (a >= 1 && a <= 4 && vel != (((a + 1) & 3) + 1)) vel = a;   // :108-115
-    if (RULES == SNK_RULES_CUT && a == 5) strike |= 1u << s;
-    if (vel == 0) continue;                                          // :119
-    const int head = env.head[s] + chain_delta((u32)(vel - 1), V);
-    int n_eat = 0;
-    u32 hitmask = 0;
-    if (RULES == SNK_RULES_CLASSIC) {
+    u32 hitmask = 0;   // classic: fruit slots to respawn; other rule-sets: number of respawns
+    int n_spawn = 0, head = 0;
+    if (env.len[s] != 0) {
+      was_alive |= 1u << s;
+      const int a = act[s];
+      int vel = env.vel[s];
+      if (a >= 1 && a <= 4 && vel != (((a + 1) & 3) + 1)) vel = a;   // :108-115
+      if (RULES == SNK_RULES_CUT && a == 5) strike |= 1u << s;
+      if (vel != 0) {                                                  // :119
+        head = env.head[s] + chain_delta((u32)(vel - 1), V);
+        int n_eat = 0;
+        if (RULES == SNK_RULES_CLASSIC) {
 #pragma unroll
-      for (int f = 0; f < 4; ++f) if (f < F && env.fruit[f] == head) { hitmask |= 1u << f; ++n_eat; }   // :126-132
-    } else {
-      n_eat = fruit_count(fs, head);
-    }
-    const int grow = env.grow[s] + 2 * n_eat;
-    int len = env.len[s];
-    if (len >= grow) len--;                                          // :134-135
-    len++;                                                           // :137
-    {  // push the new direction: segment 0 -> 1 was created by `vel`
-      u32* ch = p.chain + (e * S + s) * p.CW;
-      const int nw = (len - 1 + 15) >> 4;
-      u32 carry = env.c0[s] >> 30;
-      env.c0[s] = (env.c0[s] << 2) | (u32)(vel - 1);
-      for (int k = 1; k < nw; ++k) { const u32 w = ch[k]; ch[k] = (w << 2) | carry; carry = w >> 30; }
-    }
-    env.head[s] = head; env.len[s] = len; env.grow[s] = grow; env.vel[s] = vel;
-    if (RULES == SNK_RULES_CLASSIC) {
-      for (; hitmask; hitmask &= hitmask - 1) {                      // :139-140, half-updated world
-        const int f = __ffs(hitmask) - 1;
-        const int cell = lane_spawn<S>(p, e, env, rng, errs, st.draws);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) if (g == f) env.fruit[g] = cell;
-      }
-    } else {
-      for (int i = 0; i < n_eat; ++i) {
-        if (RULES == SNK_RULES_ADVERSARIAL && env.spare > 0) {       // snake_adversarial_env.py:138-139
-          env.spare--;
+          for (int f = 0; f < 4; ++f) if (f < F && env.fruit[f] == head) { hitmask |= 1u << f; ++n_eat; }   // :126-132
         } else {
-          const int cell = lane_spawn<S>(p, e, env, rng, errs, st.draws);
-          fruit_dec(fs, head); fruit_inc(fs, cell, errs);
+          n_eat = fruit_count(fs, head);
         }
+        const int grow = env.grow[s] + 2 * n_eat;
+        int len = env.len[s];
+        if (len >= grow) len--;                                          // :134-135
+        len++;                                                           // :137
+        {  // push the new direction: segment 0 -> 1 was created by `vel`
+          u32* ch = p.chain + (e * S + s) * p.CW;
+          const int nw = (len - 1 + 15) >> 4;
+          u32 carry = env.c0[s] >> 30;
+          env.c0[s] = (env.c0[s] << 2) | (u32)(vel - 1);
+          for (int k = 1; k < nw; ++k) { const u32 w = ch[k]; ch[k] = (w << 2) | carry; carry = w >> 30; }
+        }
+        env.head[s] = head; env.len[s] = len; env.grow[s] = grow; env.vel[s] = vel;
+        if (RULES == SNK_RULES_ADVERSARIAL) {                          // snake_adversarial_env.py:138-139: spare fruits first
+          const int use = min((int)min(env.spare, 0x7fffffffu), n_eat);
+          env.spare -= (u32)use;
+          n_spawn = n_eat - use;
+        } else if (RULES == SNK_RULES_CUT) {
+          n_spawn = n_eat;
+        }
+        moved |= 1u << s;
+        eaten[s] = n_eat;
       }
     }
-    moved |= 1u << s;
-    eaten[s] = n_eat;
+    SNK_LOGIC_MARK(0)
+    // respawns (:139-140, against the half-updated world): up to four envs per pass by the whole warp
+    for (;;) {
+      const bool need = RULES == SNK_RULES_CLASSIC ? hitmask != 0 : n_spawn > 0;
+      u32 mm = __ballot_sync(FULL, need);
+      if (!mm) break;
+      u32 raw = 0;
+      if (need && p.rng_mode != SNK_RNG_TAPE) raw = lane_philox_peek<S>(p, e, env, rng);  // all owners at once
+      while (mm) {
+        int cell;
+        if (group_spawn<S>(p, e, env, rng, raw, mm, bm, errs, st.draws, cell)) {
+          if (RULES == SNK_RULES_CLASSIC) {
+            const int f = __ffs(hitmask) - 1;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) if (g == f) env.fruit[g] = cell;
+            hitmask &= hitmask - 1;
+          } else {
+            fruit_dec(fs, head); fruit_inc(fs, cell, errs);
+            --n_spawn;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) mm &= mm - 1;  // the four owners of this pass are done
+      }
+    }
+    SNK_LOGIC_MARK(1)
   }
   // ---- is_snake_alive for all snakes on the post-move bodies, before anything is cleared (:147-164, :178-182)
   u32 empty = 0, oob = 0, hit_own = 0, hit_head = 0, hit_body = 0;
@@ -291,6 +444,7 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<
       env.spare += (u32)(env.len[j] * env.len[j]);
     }
   }
+  SNK_LOGIC_MARK(2)
   // ---- clear (:184-185), reward (:187-190), t (:192-193), done (:195), Monitor (monitor.py:57-78)
   int cells = 0;
 #pragma unroll
@@ -301,27 +455,30 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, LaneEnv<
   const bool done = env.t >= (u32)p.max_steps || main_dead;
   env.ep_ret += r0;
   env.ep_len += 1;
-  int fruits = 0;
+  if (valid) {
+    int fruits = 0;
 #pragma unroll
-  for (int s = 0; s < S; ++s) {
-    const bool d = (dead >> s) & 1;
-    const float r = s == 0 ? r0 : d ? (((was_alive >> s) & 1) ? -1.f : 0.f) : (float)eaten[s];
-    p.reward_all[e * S + s] = r;
-    fruits += eaten[s];
+    for (int s = 0; s < S; ++s) {
+      const bool d = (dead >> s) & 1;
+      const float r = s == 0 ? r0 : d ? (((was_alive >> s) & 1) ? -1.f : 0.f) : (float)eaten[s];
+      p.reward_all[e * S + s] = r;
+      fruits += eaten[s];
+    }
+    p.reward[e] = r0;
+    p.done[e] = done;
+    p.num_alive[e] = (u8)(S - __popc(dead));
+    p.fin_ret[e] = done ? env.ep_ret : 0.f;
+    p.fin_len[e] = done ? (int)env.ep_len : 0;
+    st.steps += 1.f;
+    st.fruits += (float)fruits;
+    st.deaths += (float)__popc(dead & was_alive);
+    st.cells += (float)cells;
+    if (done) {
+      st.episodes += 1.f; st.ret_sum += env.ep_ret; st.len_sum += (float)env.ep_len;
+      if (p.auto_reset) lane_reset<S, RULES>(p, e, env, rng, fs, errs, st.draws);  // subproc_vec_env.py:13-16
+    }
   }
-  p.reward[e] = r0;
-  p.done[e] = done;
-  p.num_alive[e] = (u8)(S - __popc(dead));
-  p.fin_ret[e] = done ? env.ep_ret : 0.f;
-  p.fin_len[e] = done ? (int)env.ep_len : 0;
-  st.steps += 1.f;
-  st.fruits += (float)fruits;
-  st.deaths += (float)__popc(dead & was_alive);
-  st.cells += (float)cells;
-  if (done) {
-    st.episodes += 1.f; st.ret_sum += env.ep_ret; st.len_sum += (float)env.ep_len;
-    if (p.auto_reset) lane_reset<S, RULES>(p, e, env, rng, fs, errs, st.draws);  // subproc_vec_env.py:13-16
-  }
+  SNK_LOGIC_MARK(3)
 }
 
 // The record and the actions of one env as they sit in HBM: fetched early (the loads stay in flight
@@ -413,26 +570,6 @@ __device__ __forceinline__ void lane_store(const Params& p, long long e, const L
 #pragma unroll
     for (int i = 0; i < RW / 4; ++i) g[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
   }
-}
-
-// Position of segment i without walking: the 2-bit codes before it are counted per direction with
-// popcounts, pid_i = head - V*(#(+V) - #(-V)) - (#(+1) - #(-1)).
-__device__ __forceinline__ int chain_pos(int head, u32 c0, const u32* __restrict__ ch, int V, int i) {
-  int nV = 0, n1 = 0;
-  u32 w = c0;
-  int k = 0;
-  for (; i - 16 * k > 16; ++k) {  // whole words before the one holding code i-1 (bodies longer than 17)
-    const u32 lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
-    nV += 16 - __popc(lo | hi) - __popc(hi & ~lo);
-    n1 += __popc(lo & ~hi) - __popc(lo & hi);
-    w = ch[k + 1];
-  }
-  const int r = i - 16 * k;  // 0..16 codes of word k
-  const u32 m = r >= 16 ? 0x55555555u : ((1u << (2 * r)) - 1u) & 0x55555555u;
-  const u32 lo = w & m, hi = (w >> 1) & m;
-  nV += r - __popc(lo | hi) - __popc(hi & ~lo);
-  n1 += __popc(lo & ~hi) - __popc(lo & hi);
-  return head - V * nV - n1;
 }
 
 // all C = 3K bytes of one pixel: snake s seen by every view k (self colours iff s == k)
@@ -531,4 +668,53 @@ __device__ __forceinline__ void lane_paint(const Params& p, const PaintEnv<S>& p
     }
     if (PAINT) __syncwarp();
   }
+}
+
+// Un-paint without walking: the interior of every image is black and the border white, so the warp
+// zero-fills its whole image buffer (16-byte stores) and the LPE lanes of each env redraw the border
+// spans -- [0, row + 1 px), the (last px of row x, first px of row x+1) pairs, [last px of row V-2, end).
+// Fixed cost per image (about 100 stores per lane at 8 envs of 2 views 21x21), independent of the body
+// lengths; the kernel uses it when the walk would be longer (Params::restore_thr).
+template <int K>
+__device__ __noinline__ void lane_restore(u8* tile, int n16, u8* img, int V, int sub, int LPE, int lane) {
+  constexpr int C = 3 * K, U = (C & 1) ? 1 : 2, PU = 2 * C / U;
+  uint4* t4 = reinterpret_cast<uint4*>(tile);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = lane; i < n16; i += 32) t4[i] = z;
+  __syncwarp();
+  const int RB = V * C;
+  const int n_edge = (RB + C) / U;
+  u8* bot = img + RB * (V - 1) - C;
+  for (int j = sub; j < n_edge; j += LPE) {
+    if (U == 2) { *reinterpret_cast<u16*>(img + 2 * j) = 0xffffu; *reinterpret_cast<u16*>(bot + 2 * j) = 0xffffu; }
+    else { img[j] = 0xff; bot[j] = 0xff; }
+  }
+  // rows 1..V-3: the (last px of row x, first px of row x+1) pair, one row per lane and trip
+  for (int x = 1 + sub; x <= V - 3; x += LPE) {
+    u8* q = img + x * RB + RB - C;
+#pragma unroll
+    for (int r = 0; r < PU; ++r) {
+      if (U == 2) *reinterpret_cast<u16*>(q + 2 * r) = 0xffffu; else q[r] = 0xff;
+    }
+  }
+}
+
+// Un-paint decision: lane_restore when some lane of the warp would walk more than Params::restore_thr segments
+// (warp-uniform, bit-identical result either way).  Taken BEFORE the image is painted and handed to the TMA engine,
+// so that the warp reduction is off the critical path between the engine's read and the next paint.
+template <int S>
+__device__ __forceinline__ bool lane_wants_restore(const Params& p, const int* len, int LPE) {
+  if (p.restore_thr <= 0) return false;
+  const int sh = 31 - __clz(LPE);
+  int it = 0;
+#pragma unroll
+  for (int s = 0; s < S; ++s) it += (len[s] + LPE - 1) >> sh;
+  return __reduce_max_sync(FULL, it) > p.restore_thr;
+}
+
+template <int S, int RULES, int K>
+__device__ __forceinline__ void lane_unpaint(const Params& p, const PaintEnv<S>& pe, long long e_owner, int sub, int LPE, u8* tile, int tile_bytes,
+                                             u8* img, int lane, bool restore) {
+  if (restore) lane_restore<K>(tile, tile_bytes >> 4, img, p.V, sub, LPE, lane);
+  else lane_paint<S, RULES, K, false>(p, pe, e_owner, sub, LPE, img);
 }

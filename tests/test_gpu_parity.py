@@ -330,6 +330,45 @@ def test_lane_kernel_variants_match_oracle(sb, monkeypatch, variant):
     monkeypatch.delenv("SNK_LANE")
 
 
+@pytest.mark.parametrize("thr,variant", [(1, "fused"), (3, "fused"), (1, "ws"), (2, "split")])
+def test_lane_restore_unpaint_matches_oracle(sb, monkeypatch, thr, variant):
+    """Un-paint by zero-fill + border redraw (Params::restore_thr) instead of the second chain walk: same bytes.
+    thr = 1 restores after almost every image, thr = 3 mixes both forms inside one launch; covers 1 view (3-byte
+    pixels, byte-wide border stores), 2 and 3 views, all TE / LPE shapes and long injected bodies."""
+    monkeypatch.setenv("SNK_RESTORE_THR", str(thr))
+    monkeypatch.setenv("SNK_LANE", variant)
+    for rules, S, D, N, steps in (("classic", 2, 19, 1000, 150), ("classic", 1, 10, 500, 100), ("classic", 1, 2, 70, 40),
+                                  ("adversarial", 3, 10, 300, 150), ("cut", 3, 14, 300, 150), ("classic", 4, 14, 100, 100)):
+        kw = dict(size=D, n_snakes=S, rules=rules, seed=17)
+        env = sb.SnakeVecEnv(N, **kw)
+        assert env.launch_info()["kernel"] == "k_step_lane", (rules, S, D, env.launch_info())
+        co = c_oracle.COracle(N, **kw)
+        assert np.array_equal(env.reset().cpu().numpy(), co.reset())
+        for t in range(steps):
+            a = c_oracle.gen_actions(co.cfg, t, 5, env.action_space.n)
+            _compare_step(env, co, a, "restore thr %d %s S%d D%d step %d" % (thr, rules, S, D, t), check_state=(t % 25 == 0))
+        env.close()
+    # long bodies: 20-70 segments
+    N = 96
+    kw = dict(size=19, n_snakes=2, rules="classic", seed=31)
+    env = sb.SnakeVecEnv(N, **kw)
+    co = c_oracle.COracle(N, **kw)
+    rng = np.random.RandomState(9)
+    blob = helpers.random_long_snake_states(co.lay, co.cfg, rng)
+    co.load_state(blob)
+    env.load_state_blob(blob)
+    import torch
+    env.reset(mask=torch.zeros(N, dtype=torch.bool, device=env.device))
+    assert np.array_equal(env.obs.cpu().numpy(), co.observe())
+    for t in range(80):
+        a = rng.randint(0, 5, size=(N, 2)).astype(np.int8)
+        a[rng.rand(N, 2) < 0.6] = 0
+        _compare_step(env, co, a, "restore long step %d" % t, check_state=(t % 20 == 0))
+    env.close()
+    monkeypatch.delenv("SNK_RESTORE_THR")
+    monkeypatch.delenv("SNK_LANE")
+
+
 @pytest.mark.parametrize("rules,S,D,kernel", [("classic", 2, 19, None), ("cut", 3, 19, None), ("adversarial", 2, 14, None),
                                                ("classic", 2, 19, "tile"), ("cut", 3, 14, "dense"), ("classic", 4, 30, "rows")])
 def test_injected_long_snakes(sb, monkeypatch, rules, S, D, kernel):
