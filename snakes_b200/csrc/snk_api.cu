@@ -153,6 +153,7 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   p.G = 16 / gcd(p.E, 16);
   p.grid_stride = (int)align16((size_t)p.VV);
   p.bm_words = (D * D + 31) / 32;
+  p.magicV = 65536u / (uint32_t)V + 1u; p.magicD = 65536u / (uint32_t)D + 1u;
   p.max_steps = h->cfg.max_steps; p.auto_reset = cfg->auto_reset != 0; p.rng_mode = cfg->rng_mode;
   p.N = N; p.env_id_base = cfg->env_id_base; p.seed = cfg->seed;
 
@@ -205,8 +206,13 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     // ... unless there are too few 32-env batches to give every SM a few (4 096 envs of 2x10x10: one
     // batch per SM at most): then a warp that steps AND paints its batch has the shortest critical path
     // (13.8 us vs 19.0 us per step)
-    plan.ws = plan.kind == KIND_LANE && (lv ? !strcmp(lv, "ws") : (p.E < 2048 && (N + 31) / 32 >= 2LL * h->n_sm));
-    plan.split = plan.kind == KIND_LANE && lv && !strcmp(lv, "split");
+    // Since the respawns became warp-cooperative function calls the register-capped warp-specialised kernel pays for
+    // them in spills, and for S >= 2 the two-kernel form (logic at full occupancy, then the observation writer) is the
+    // fastest small-image form (65 536 envs, 10x10: 3 snakes cut 53.0 vs 61.3 us, 3 snakes classic 44.0 vs 48.8,
+    // 2 snakes 34.6 vs 38.8; 1 M envs cut 648 vs 751 us); a single snake stays warp-specialised (23.6 vs 29.2 us).
+    const bool small_image = p.E < 2048 && (N + 31) / 32 >= 2LL * h->n_sm;
+    plan.ws = plan.kind == KIND_LANE && (lv ? !strcmp(lv, "ws") : (small_image && S == 1));
+    plan.split = plan.kind == KIND_LANE && (lv ? !strcmp(lv, "split") : (small_image && S > 1));
     { const char* pd = getenv("SNK_PDL"); plan.pdl = !(pd && !strcmp(pd, "0")); }
 
     const char* lw = getenv("SNK_LOGIC_WARPS");

@@ -132,7 +132,7 @@ struct SpawnBodies {  // the bodies of one env as the lane that owns it holds th
 
 // phase 1: bitmaps of the (up to four) owners of this pass; returns the number of free cells to the served owners
 template <int S>
-__device__ __noinline__ u32 spawn_totals(SpawnBodies<S> me, u32 mm, u32* bm, const u32* chain, int CW, int V, const u32* cellinfo, int nW, int DD) {
+__device__ __noinline__ u32 spawn_totals(SpawnBodies<S> me, u32 mm, u32* bm, const u32* chain, int CW, int V, int D, u32 magicV, int nW, int DD) {
   const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
   u32 m = mm;
   for (int t = 0; t < g; ++t) m &= m - 1;
@@ -150,7 +150,11 @@ __device__ __noinline__ u32 spawn_totals(SpawnBodies<S> me, u32 mm, u32* bm, con
     const u32 c0 = __shfl_sync(FULL, me.c0[s], src);
     const u32* ch = chain + (eo * S + s) * CW;
     for (int i = sub; i < l; i += 8) {
-      const u32 idx = __ldg(cellinfo + chain_pos(h, c0, ch, V, i)) & 0x7fffffffu;
+      // y*D + x, not bounds-checked (:209): an out-of-board head aliases another cell or nothing, exactly as cellinfo
+      // tabulates it -- computed here because the 27 KB of L1 left beside the images rarely holds the table
+      const u32 pid = (u32)chain_pos(h, c0, ch, V, i);
+      const u32 px = (pid * magicV) >> 16, py = pid - px * (u32)V;
+      const u32 idx = (u32)(((int)py - 1) * D + (int)px - 1);
       if (idx < (u32)DD) atomicOr(&b[idx >> 5], 1u << (idx & 31));
     }
   }
@@ -176,7 +180,7 @@ __device__ __noinline__ u32 spawn_totals(SpawnBodies<S> me, u32 mm, u32* bm, con
 }
 
 // phase 2: k = the owner's draw (or -1); returns the k-th free cell (y-major order) to the served owners
-static __device__ __noinline__ int spawn_pick(int k, u32 mm, u32* bm, const u16* idx2pid) {
+static __device__ __noinline__ int spawn_pick(int k, u32 mm, u32* bm, int V, int D, u32 magicD) {
   const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
   u32 m = mm;
   for (int t = 0; t < g; ++t) m &= m - 1;
@@ -203,7 +207,8 @@ static __device__ __noinline__ int spawn_pick(int k, u32 mm, u32* bm, const u16*
       if (!found && r < cj) { idx = (4 * sub + j) * 32 + (int)__fns(fr[j], 0, r + 1); found = true; }
       r -= cj;
     }
-    bm[132 + g] = idx2pid[idx];
+    const u32 y = ((u32)idx * magicD) >> 16, x = (u32)idx - y * (u32)D;  // cell (idx % D, idx // D) (:216)
+    bm[132 + g] = (x + 1) * (u32)V + y + 1;
   }
   __syncwarp();
   const int rank = __popc(mm & ((1u << lane) - 1u));
@@ -221,14 +226,14 @@ __device__ __forceinline__ bool group_spawn(const Params& p, long long e, LaneEn
   me.e = e;
 #pragma unroll
   for (int s = 0; s < S; ++s) { me.head[s] = env.head[s]; me.len[s] = env.len[s]; me.c0[s] = env.c0[s]; }
-  const u32 total = spawn_totals<S>(me, mm, bm, p.chain, p.CW, p.V, p.cellinfo, p.bm_words, p.D * p.D);
+  const u32 total = spawn_totals<S>(me, mm, bm, p.chain, p.CW, p.V, p.D, p.magicV, p.bm_words, p.D * p.D);
   const bool served = ((mm >> lane) & 1u) && __popc(mm & ((1u << lane) - 1u)) < 4;
   int k = -1;
   if (served && total > 0) {
     if (p.rng_mode == SNK_RNG_TAPE) k = (int)lane_draw<S>(p, e, env, rng, total, errs, draws);
     else { env.ctr++; draws += 1.f; k = (int)__umulhi(raw, total); }
   }
-  const int c = spawn_pick(k, mm, bm, p.idx2pid);
+  const int c = spawn_pick(k, mm, bm, p.V, p.D, p.magicD);
   cell = k >= 0 ? c : p.V + 1;                     // (0,0), no draw, when nothing is free (:212-215)
   return served;
 }

@@ -130,3 +130,13 @@ def test_tile_images_layout():
     assert big.shape == (3 * 2, 2 * 3, 3)
     assert big[0, 0, 0] == 1 and big[0, 3, 0] == 2 and big[2, 0, 0] == 3 and big[2, 3, 0] == 4 and big[4, 0, 0] == 5
     assert not big[4:, 3:].any()
+
+
+def test_lane_kernel_reciprocal_constants_are_exact():
+    """group_spawn (snk_lane.cuh) divides padded ids by V and board indices by D with (n * (65536 // d + 1)) >> 16;
+    exact for every board the lane family accepts (D <= 32, snk_api.cu launch plan)."""
+    for D in range(1, 33):
+        V = D + 2
+        mV, mD = 65536 // V + 1, 65536 // D + 1
+        assert all((n * mV) >> 16 == n // V for n in range(V * V))
+        assert all((n * mD) >> 16 == n // D for n in range(D * D))

@@ -15,7 +15,8 @@ def report(tag, env, us, N):
     st = env.stats(False)
     sl = st["body_cells"] / max(st["env_steps"], 1)
     ab = env.algorithmic_bytes_per_step(sl)
-    print("%-28s %7.1f us  sumL %5.1f  frac %.3f" % (tag, us, sl, ab * N / us / 1e3 / 6548.2), flush=True)
+    es = max(st["env_steps"], 1)
+    print("%-28s %7.1f us  sumL %5.1f  frac %.3f  (per env-step: %.3f fruits, %.3f draws, %.4f episodes)" % (tag, us, sl, ab * N / us / 1e3 / 6548.2, st["fruits"] / es, st["draws"] / es, st["episodes"] / es), flush=True)
 
 def short(N, reps=3, **kw):
     env = snakes_b200.SnakeVecEnv(N, **kw); env.reset()
