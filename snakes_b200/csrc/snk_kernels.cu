@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(64) k_lane_paint(const Params p) {
     const PaintEnv<S> nxt = paint_env_from_memory<S>(p, next < n_items ? next * TE + slot : p.N);
     const long long e0 = item * TE;
     const bool restore = lane_wants_restore<S>(p, cur.len, LPE);
-    lane_paint<S, RULES, K, true>(p, cur, e0 + slot, sub, LPE, img);
+    lane_paint<S, RULES, K>(p, cur, e0 + slot, sub, LPE, img, true);
     fence_async_smem();
     __syncwarp();
     store_image(p, tile, tile_bytes, e0, lane);
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(160, 5) k_step_lane_ws(const Params p) {
         __threadfence_block();
         const PaintEnv<S> pe = paint_env_from_memory<S>(p, e0 + slot);
         const bool restore = lane_wants_restore<S>(p, pe.len, LPE);
-        lane_paint<S, RULES, K, true>(p, pe, e0 + slot, sub, LPE, img);
+        lane_paint<S, RULES, K>(p, pe, e0 + slot, sub, LPE, img, true);
         fence_async_smem();
         __syncwarp();
         store_image(p, tile, tile_bytes, e0, lane);
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
       const long long e0 = b * 32 + (long long)q * TE;
       if (e0 >= p.N) break;
       const PaintEnv<S> pe = paint_env_from_lane<S>(env, valid, q * TE + slot);
-      lane_paint<S, RULES, K, true>(p, pe, e0 + slot, sub, LPE, img);
+      lane_paint<S, RULES, K>(p, pe, e0 + slot, sub, LPE, img, true);
       fence_async_smem();  // generic-proxy writes -> visible to the async (TMA) proxy
       __syncwarp();
 #ifdef SNK_PHASE_TIMING

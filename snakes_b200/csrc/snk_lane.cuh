@@ -278,18 +278,25 @@ __device__ __forceinline__ void lane_reset(const Params& p, long long e, LaneEnv
   if (RULES != SNK_RULES_CLASSIC) {
     for (int w = 0; w < p.GBW; ++w) fs.bits[w] = 0;
   }
+  // the draws in a rolled loop (two inlined copies of lane_draw instead of twelve: the kernel lives off the instruction
+  // cache), the cells parked in a small local array, then dealt out in the reference's interleaved order
+  int cells[8];
+  const int nc = S + F;
+#pragma unroll 1
+  for (int c = 0; c < nc; ++c) {
+    const int x = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
+    const int y = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
+    cells[c] = (x + 1) * V + (y + 1);
+  }
+  int r = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (i < S) {
-      const int x = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
-      const int y = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
-      env.head[i < S ? i : 0] = (x + 1) * V + (y + 1);
+      env.head[i < S ? i : 0] = cells[r++];
       env.len[i < S ? i : 0] = 1; env.grow[i < S ? i : 0] = 3; env.vel[i < S ? i : 0] = 0; env.c0[i < S ? i : 0] = 0;
     }
     if (i < F) {
-      const int x = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
-      const int y = (int)lane_draw<S>(p, e, env, rng, (u32)p.D, errs, draws);
-      const int pid = (x + 1) * V + (y + 1);
+      const int pid = cells[r++];
       if (RULES == SNK_RULES_CLASSIC) env.fruit[i] = pid; else fruit_inc(fs, pid, errs);
     }
   }
@@ -578,11 +585,11 @@ __device__ __forceinline__ void lane_store(const Params& p, long long e, const L
 }
 
 // all C = 3K bytes of one pixel: snake s seen by every view k (self colours iff s == k)
-template <int S, int K, bool PAINT>
-__device__ __forceinline__ void put_pixel(u8* px, int s, bool is_head) {
+template <int S, int K>
+__device__ __forceinline__ void put_pixel(u8* px, int s, bool is_head, bool paint) {
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const u32 rgb = PAINT ? snake_rgb(s == k, is_head) : 0u;
+    const u32 rgb = paint ? snake_rgb(s == k, is_head) : 0u;
     px[3 * k] = (u8)rgb; px[3 * k + 1] = (u8)(rgb >> 8); px[3 * k + 2] = (u8)(rgb >> 16);
   }
 }
@@ -640,16 +647,18 @@ __device__ __forceinline__ PaintEnv<S> paint_env_from_memory(const Params& p, lo
 // The reference's paint order (fruits, then snakes by index, get_ob_for_snake :35-58) is kept by a
 // __syncwarp between the groups; within a group two items never overlap with different colours.
 // Out-of-board cells are skipped (the reference paints them under the border, :52-56).
-template <int S, int RULES, int K, bool PAINT>
-__device__ __forceinline__ void lane_paint(const Params& p, const PaintEnv<S>& pe, long long e_owner, int sub, int LPE, u8* img) {
+// `paint` is a run-time flag: one copy of the walk serves painting and un-painting (code size, see lane_reset).
+template <int S, int RULES, int K>
+__device__ __forceinline__ void lane_paint(const Params& p, const PaintEnv<S>& pe, long long e_owner, int sub, int LPE, u8* img, bool paint) {
   constexpr int C = 3 * K;
   const int V = p.V, F = p.F;
+  const u8 red = paint ? 255 : 0;
   if (RULES == SNK_RULES_CLASSIC) {
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
       if (pe.valid && f < F && (f & (LPE - 1)) == sub) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) img[pe.fruit[f] * C + 3 * k] = PAINT ? 255 : 0;
+        for (int k = 0; k < K; ++k) img[pe.fruit[f] * C + 3 * k] = red;
       }
     }
   } else if (pe.valid) {
@@ -659,19 +668,19 @@ __device__ __forceinline__ void lane_paint(const Params& p, const PaintEnv<S>& p
         const int pid = 32 * w + __ffs(bits) - 1;
         if (!(__ldg(p.cellinfo + pid) >> 31)) {
 #pragma unroll
-          for (int k = 0; k < K; ++k) img[pid * C + 3 * k] = PAINT ? 255 : 0;
+          for (int k = 0; k < K; ++k) img[pid * C + 3 * k] = red;
         }
       }
     }
   }
-  if (PAINT) __syncwarp();
+  __syncwarp();
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     if (pe.valid) {
       const u32* ch = p.chain + (e_owner * S + s) * p.CW;
-      for (int i = sub; i < pe.len[s]; i += LPE) put_pixel<S, K, PAINT>(img + chain_pos(pe.head[s], pe.c0[s], ch, V, i) * C, s, i == 0);
+      for (int i = sub; i < pe.len[s]; i += LPE) put_pixel<S, K>(img + chain_pos(pe.head[s], pe.c0[s], ch, V, i) * C, s, i == 0, paint);
     }
-    if (PAINT) __syncwarp();
+    __syncwarp();
   }
 }
 
@@ -721,5 +730,5 @@ template <int S, int RULES, int K>
 __device__ __forceinline__ void lane_unpaint(const Params& p, const PaintEnv<S>& pe, long long e_owner, int sub, int LPE, u8* tile, int tile_bytes,
                                              u8* img, int lane, bool restore) {
   if (restore) lane_restore<K>(tile, tile_bytes >> 4, img, p.V, sub, LPE, lane);
-  else lane_paint<S, RULES, K, false>(p, pe, e_owner, sub, LPE, img);
+  else lane_paint<S, RULES, K>(p, pe, e_owner, sub, LPE, img, false);
 }
