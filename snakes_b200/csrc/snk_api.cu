@@ -239,6 +239,7 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     }
     plan.block = plan.ws ? 32 * (p.PW + logic_warps) : 64;
     plan.smem = (size_t)2 * p.tile_stride;
+    { const char* xs = getenv("SNK_EXTRA_SMEM"); if (xs) plan.smem += (size_t)atoi(xs); }  // experiment: fewer resident CTAs (image buffers) per SM
     p.n_groups = (N + 31) / 32;
   } else if (plan.kind == KIND_TILE) {
     p.W = W; plan.block = 32 * W; plan.smem = smem_tile;
