@@ -587,10 +587,19 @@ __device__ __forceinline__ void lane_store(const Params& p, long long e, const L
 // all C = 3K bytes of one pixel: snake s seen by every view k (self colours iff s == k)
 template <int S, int K>
 __device__ __forceinline__ void put_pixel(u8* px, int s, bool is_head, bool paint) {
+  if (K % 2 == 0) {  // 6 bytes per pair of views at an even address: three 16-bit stores instead of six bytes
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const u32 rgb = paint ? snake_rgb(s == k, is_head) : 0u;
-    px[3 * k] = (u8)rgb; px[3 * k + 1] = (u8)(rgb >> 8); px[3 * k + 2] = (u8)(rgb >> 16);
+    for (int m = 0; m < K / 2; ++m) {
+      const u32 a = paint ? snake_rgb(s == 2 * m, is_head) : 0u, b = paint ? snake_rgb(s == 2 * m + 1, is_head) : 0u;
+      u16* q = reinterpret_cast<u16*>(px + 6 * m);
+      q[0] = (u16)a; q[1] = (u16)((a >> 16) | ((b & 0xffu) << 8)); q[2] = (u16)(b >> 8);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const u32 rgb = paint ? snake_rgb(s == k, is_head) : 0u;
+      px[3 * k] = (u8)rgb; px[3 * k + 1] = (u8)(rgb >> 8); px[3 * k + 2] = (u8)(rgb >> 16);
+    }
   }
 }
 
