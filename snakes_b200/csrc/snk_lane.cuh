@@ -109,6 +109,26 @@ __device__ __forceinline__ int chain_pos(int head, u32 c0, const u32* __restrict
   return head - V * nV - n1;
 }
 
+// chain_pos for a lane that visits segments in increasing order (i, i + LPE, ...): the whole words before the current
+// one are folded into `base` once per word instead of once per segment.
+struct ChainCursor {
+  int base, k;
+  u32 w;
+  __device__ __forceinline__ ChainCursor(int head, u32 c0) : base(head), k(0), w(c0) {}
+  __device__ __forceinline__ int at(const u32* ch, int V, int i) {
+    while (i - 16 * k > 16) {
+      const u32 lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+      base -= V * (16 - __popc(lo | hi) - __popc(hi & ~lo)) + __popc(lo & ~hi) - __popc(lo & hi);
+      w = ch[k + 1];
+      ++k;
+    }
+    const int r = i - 16 * k;  // 0..16 codes of word k
+    const u32 m = r >= 16 ? 0x55555555u : ((1u << (2 * r)) - 1u) & 0x55555555u;
+    const u32 lo = w & m, hi = (w >> 1) & m;
+    return base - V * (r - __popc(lo | hi) - __popc(hi & ~lo)) - (__popc(lo & ~hi) - __popc(lo & hi));
+  }
+};
+
 // safe_choose_cell (:202-217), warp-cooperative.  Under a policy that eats, about six lanes of every warp respawn a
 // fruit on every step; a one-lane form (a serial walk of all bodies with a bitmap in local memory, about 5 k cycles;
 // the first version of this kernel) then sits on the warp's critical path.  Here the warp serves up to FOUR envs
@@ -149,10 +169,11 @@ __device__ __noinline__ u32 spawn_totals(SpawnBodies<S> me, u32 mm, u32* bm, con
     if (!active) l = 0;
     const u32 c0 = __shfl_sync(FULL, me.c0[s], src);
     const u32* ch = chain + (eo * S + s) * CW;
+    ChainCursor cur(h, c0);
     for (int i = sub; i < l; i += 8) {
       // y*D + x, not bounds-checked (:209): an out-of-board head aliases another cell or nothing, exactly as cellinfo
       // tabulates it -- computed here because the 27 KB of L1 left beside the images rarely holds the table
-      const u32 pid = (u32)chain_pos(h, c0, ch, V, i);
+      const u32 pid = (u32)cur.at(ch, V, i);
       const u32 px = (pid * magicV) >> 16, py = pid - px * (u32)V;
       const u32 idx = (u32)(((int)py - 1) * D + (int)px - 1);
       if (idx < (u32)DD) atomicOr(&b[idx >> 5], 1u << (idx & 31));
@@ -687,7 +708,8 @@ __device__ __forceinline__ void lane_paint(const Params& p, const PaintEnv<S>& p
   for (int s = 0; s < S; ++s) {
     if (pe.valid) {
       const u32* ch = p.chain + (e_owner * S + s) * p.CW;
-      for (int i = sub; i < pe.len[s]; i += LPE) put_pixel<S, K>(img + chain_pos(pe.head[s], pe.c0[s], ch, V, i) * C, s, i == 0, paint);
+      ChainCursor cur(pe.head[s], pe.c0[s]);
+      for (int i = sub; i < pe.len[s]; i += LPE) put_pixel<S, K>(img + cur.at(ch, V, i) * C, s, i == 0, paint);
     }
     __syncwarp();
   }
