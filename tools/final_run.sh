@@ -18,3 +18,7 @@ PY
 ncu --set full --clock-control none --import-source on -k regex:k_step_rows -s 10 -c 1 -o gpurun_out/final_rows -f python /tmp/rows_probe.py > gpurun_out/final_ncu3.log 2>&1; echo "rows full rc=$?"
 python tools/probe.py > gpurun_out/final_probe.txt 2>&1; cat gpurun_out/final_probe.txt | cut -c1-170
 python tools/ab_rows.py 32768 > gpurun_out/final_rows_32768.txt 2>&1; cat gpurun_out/final_rows_32768.txt | cut -c1-120
+# long-body regime (fruit-seeking policy): one full capture of the lane kernel, and what the box sustains for pure writes
+python tools/probe_long_ncu.py && ncu --set full --clock-control none --import-source on -k regex:k_step_lane -s 403 -c 1 -o gpurun_out/final_long -f python tools/probe_long_ncu.py > gpurun_out/final_ncu_long.log 2>&1; echo "long full rc=$?"
+python tools/bw_probe.py > gpurun_out/final_bw_probe.txt 2>&1; tail -2 gpurun_out/final_bw_probe.txt
+python tools/ab.py short long c3 > gpurun_out/final_ab.txt 2>&1; grep -E "^short|^long" gpurun_out/final_ab.txt | cut -c1-100
