@@ -430,12 +430,15 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, bool val
     if (env.len[s] == 0) empty |= 1u << s;
     else if (__ldg(p.cellinfo + env.head[s]) >> 31) oob |= 1u << s;
   }
+  int live_head[S];  // head of a live snake, or an id no cell has: one compare per segment and snake in the walks
+#pragma unroll
+  for (int s = 0; s < S; ++s) live_head[s] = env.len[s] ? env.head[s] : -1;
 #pragma unroll
   for (int j = 0; j < S; ++j) {
     chain_walk(env.head[j], env.len[j], env.c0[j], chain_e + j * p.CW, V, [&](int i, int pid) {
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        if (env.len[s] && pid == env.head[s]) {
+        if (pid == live_head[s]) {
           if (i == 0) { if (j != s) hit_head |= 1u << s; }
           else if (j == s) hit_own |= 1u << s;
           else hit_body |= 1u << s;
