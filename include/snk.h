@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SNK_VERSION 100 /* 0.1.0 */
+#define SNK_VERSION 200 /* 0.2.0 */
 
 /* error codes */
 #define SNK_OK 0
@@ -37,6 +37,7 @@ extern "C" {
 #define SNK_ECUDA (-2)    /* CUDA runtime failure (text in snk_last_error) */
 #define SNK_ENOMEM (-3)
 #define SNK_ESTATE (-4)   /* device-side error flag raised (see SNK_DEVERR_*) */
+#define SNK_ECOMM (-5)    /* NCCL missing or an NCCL call failed (text in snk_last_error) */
 
 /* device error flags (sticky; read + cleared by snk_check_errors) */
 #define SNK_DEVERR_TAPE_UNDERRUN 1u   /* replay tape exhausted for some env */
@@ -65,7 +66,7 @@ extern "C" {
 typedef struct snk_config {
   int32_t size;        /* D, 2..254 */
   int32_t n_snakes;    /* S, 1..32 */
-  int32_t n_fruits;    /* F, 0..64; the reference uses F = S (snake_multiple_test.py:223-225) */
+  int32_t n_fruits;    /* F, 0..32; the reference uses F = S (snake_multiple_test.py:223-225) */
   int32_t n_views;     /* K, 1..32; 0 = S.  SnakeEnv emits K = 3 (snake_multiple_test.py:93-95) */
   int32_t rules;       /* SNK_RULES_* */
   int32_t max_steps;   /* episode cap, reference 2000 (snake_multiple_test.py:195); 0 = 2000 */
@@ -74,7 +75,7 @@ typedef struct snk_config {
   int32_t device;      /* CUDA device ordinal */
   int32_t rng_mode;    /* SNK_RNG_* */
   int64_t num_envs;    /* N, envs held by THIS handle */
-  int64_t env_id_base; /* global id of this handle's env 0 (shard offset; keys the RNG) */
+  int64_t env_id_base; /* global id of this handle's env 0 (shard offset; keys the RNG); >= 0, base + N <= 2^32 */
   uint64_t seed;
 } snk_config;
 
@@ -92,6 +93,8 @@ typedef struct snk_buffers {
   double* d_stats;         /* [SNK_NSTATS] running sums since snk_reset_stats */
   size_t obs_bytes;        /* N*H*W*3K */
   int32_t obs_h, obs_w, obs_c;
+  uint8_t* d_info_block;   /* d_done, d_num_alive, d_episode_return, d_episode_len live in this one block (in this */
+  size_t info_block_bytes; /* order, each 16-byte aligned): one copy snapshots a step's infos */
 } snk_buffers;
 
 /* indices into d_stats / snk_get_stats */
@@ -128,8 +131,12 @@ typedef struct snk_handle snk_handle;
 int snk_version(void);
 const char* snk_last_error(void);
 
-/* gym.make(id) + env.__init__(**kwargs) + env.seed()  (utils.py:37-39), for N envs at once. */
+/* gym.make(id) + env.__init__(**kwargs) + env.seed()  (utils.py:37-39), for N envs at once.
+ * snk_create reads ONE environment variable, SNK_DEBUG: a comma-separated key=value list of experiment switches
+ * (kernel family, lane-path form, L2 policies ...).  None of them changes results; unset is the
+ * production configuration.  snk_create_ex takes that string explicitly (NULL = production) and reads no environment. */
 int snk_create(const snk_config* cfg, snk_handle** out);
+int snk_create_ex(const snk_config* cfg, const char* debug_opts, snk_handle** out);
 /* VecEnv.close()  (subproc_vec_env.py:73-83). */
 int snk_destroy(snk_handle* h);
 int snk_get_config(const snk_handle* h, snk_config* out);
@@ -151,6 +158,23 @@ int snk_step(snk_handle* h, const int8_t* d_actions, void* stream);
  * Any of the h_ output pointers may be NULL to skip that copy.  Host buffers should be pinned. */
 int snk_step_host(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, float* h_reward,
                   uint8_t* h_done, uint8_t* h_num_alive, void* stream);
+/* Same, but h_obs receives only the first n_views_out views of every pixel, packed as [N][H][W][3 n_views_out]
+ * (1 <= n_views_out <= 4, or 0 / K for all views).  The reference learner keeps view 0 alone in its rollout
+ * (ppo_multi_agent_new.py:181, `obs[..., 0:3]`), so with n_views_out = 1 the D2H copy carries 1/K of the bytes; the
+ * views are gathered on the device by a small kernel first. */
+int snk_step_host_views(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, int32_t n_views_out, float* h_reward,
+                        uint8_t* h_done, uint8_t* h_num_alive, void* stream);
+/* VecEnv.step_async proper: enqueues the H2D copy, the step and the D2H copies and returns; the caller synchronises
+ * `stream` (VecEnv.step_wait) before reading the host buffers. */
+int snk_step_host_async(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, int32_t n_views_out, float* h_reward,
+                        uint8_t* h_done, uint8_t* h_num_alive, void* stream);
+
+/* Pinned host memory for the h_ buffers above, placed on the NUMA node the handle's GPU is attached to (sysfs
+ * numa_node of its PCI device; pages bound with set_mempolicy around cudaHostAlloc).  With one process per GPU this
+ * keeps every rank's D2H stream on its own socket.  *numa_node (may be NULL) receives the node, or -1 when the
+ * placement could not be applied (the memory is still pinned).  Freed by snk_host_free or snk_destroy. */
+int snk_host_alloc(snk_handle* h, size_t bytes, void** out, int32_t* numa_node);
+int snk_host_free(snk_handle* h, void* ptr);
 
 /* Write observations straight into a caller-owned device buffer (e.g. slot t of the learner's
  * rollout buffer, ppo_multi_agent_new.py:181) instead of the handle's own d_obs.
@@ -165,6 +189,24 @@ int snk_set_obs_target(snk_handle* h, uint8_t* d_obs, size_t bytes);
  * handle's own buffers (snk_get_buffers) hold the last step, as after T calls of snk_step. */
 int snk_rollout(snk_handle* h, const int8_t* d_actions, int32_t T, uint8_t* d_obs, float* d_reward,
                 uint8_t* d_done, void* stream);
+
+/* The step loop as ONE launch: T consecutive steps captured into a CUDA graph (kernel nodes linked by programmatic
+ * dependent-launch edges, plus, after snk_comm_init, one NCCL all-reduce node per step on a forked branch).  Replaces
+ * the Python `for _ in range(self.nsteps): ... self.env.step(actions)` loop of Runner.run (ppo_multi_agent_new.py:178-198)
+ * for pre-sampled / scripted action streams, and is what snk_rollout launches internally (it caches the graph of its
+ * last argument set).  Step t reads action batch t % n_batches of d_actions (int8 [n_batches][N][S]).  d_obs / d_reward /
+ * d_done as in snk_rollout, each may be NULL (the handle's own buffers, or the snk_set_obs_target target current at
+ * creation, are then written by every step).  flags: SNK_GRAPH_SYNC_BACK copies the last rollout slot back into the
+ * handle's own buffers.  A graph stays valid while the handle and the buffers it was created with live. */
+#define SNK_GRAPH_SYNC_BACK 1u
+typedef struct snk_graph snk_graph;
+int snk_graph_create(snk_handle* h, const int8_t* d_actions, int32_t n_batches, int32_t T, uint8_t* d_obs,
+                     float* d_reward, uint8_t* d_done, uint32_t flags, snk_graph** out);
+/* The scripted fruit-seeking policy in the loop: every step is the policy kernel (snk_gen_scripted_actions with step index
+ * step0 + t, reading the state the previous step left) followed by the step kernel, T times, one launch. */
+int snk_graph_create_scripted(snk_handle* h, int32_t T, uint64_t step0, uint64_t seed, int32_t eps_permille, snk_graph** out);
+int snk_graph_launch(snk_graph* g, void* stream);
+int snk_graph_destroy(snk_graph* g);
 
 /* Generalised advantage estimation over a rollout, on the device (the numpy loop at the end of
  * Runner.run, ppo_multi_agent_new.py:205-218), bit-exact with that loop's mixed precision: float32
@@ -185,6 +227,11 @@ int snk_set_draw_tape(snk_handle* h, const uint32_t* h_vals, const uint32_t* h_b
 /* Canonical state (parity tests, checkpoint / resume).  Synchronous. */
 int snk_state_layout_of(const snk_config* cfg, snk_state_layout* out);
 int snk_dump_state(snk_handle* h, void* h_dst, size_t bytes);
+/* Envs [first, first + count) only, as the blob of a `count`-env configuration (snk_state_layout_of with num_envs =
+ * count): parity checks of a slice of a large batch without moving the whole state. */
+int snk_dump_state_range(snk_handle* h, int64_t first, int64_t count, void* h_dst, size_t bytes);
+/* Rejects (SNK_ESTATE, offending snakes left empty) bodies longer than the board, cell ids outside the padded grid,
+ * velocity codes above 4 and consecutive segments that are not adjacent cells. */
 int snk_load_state(snk_handle* h, const void* h_src, size_t bytes);
 
 /* Episode statistics (Monitor's aggregate role).  snk_get_stats synchronises `stream`. */
@@ -192,6 +239,24 @@ int snk_get_stats(snk_handle* h, double* h_stats /*[SNK_NSTATS]*/, void* stream)
 int snk_reset_stats(snk_handle* h, void* stream);
 /* Reads and clears the sticky device error flags (synchronises `stream`). */
 int snk_check_errors(snk_handle* h, uint32_t* flags, void* stream);
+
+/* The path's ONE collective: with envs sharded over G GPUs, one process and one handle per GPU,
+ * every step's local statistics vector is summed over the ranks -- Monitor's per-step episode records
+ * (monitor.py:57-78, collected every step by Runner.run, ppo_multi_agent_new.py:189-192) in aggregate.  After
+ * snk_comm_init each snk_step / graph step ends with the last CTA copying the handle's running sums into a snapshot
+ * slot; a high-priority side stream all-reduces that slot (ncclAllReduce, 8 doubles, NVLink / NVSwitch) while the next
+ * step runs, and the result is read one step late.  No other inter-GPU traffic exists on the path.
+ *   snk_comm_unique_id  rank 0 creates the 128-byte NCCL id; the caller ships it to the other ranks (any channel).
+ *   snk_comm_init       collective over all ranks; NCCL is bound at run time (dlopen of libnccl.so.2), no link dependency.
+ *   snk_get_stats_global  sums over all ranks as of the last completed reduction (synchronises `stream`); without a
+ *                       communicator it equals snk_get_stats. */
+int snk_comm_unique_id(uint8_t* out128);
+int snk_comm_init(snk_handle* h, const uint8_t* id128, int32_t n_ranks, int32_t rank);
+int snk_get_stats_global(snk_handle* h, double* h_stats /*[SNK_NSTATS]*/, void* stream);
+int snk_comm_info(const snk_handle* h, int32_t* out /*[4]: ranks, rank, all-reduces issued, NCCL version code*/);
+/* Mean duration (microseconds, CUDA events on the side stream) of `iters` back-to-back all-reduces of the statistics
+ * vector: the latency bench.py reports for the collective.  Collective over all ranks; synchronises the device. */
+int snk_comm_bench(snk_handle* h, int32_t iters, double* mean_us);
 
 /* Synthetic uniform action stream for benchmarks: Philox key (seed, global env id), stream 1,
  * counter = step * S + snake, value in [0, n_actions).  d_actions: int8 [N][S]. */
@@ -210,6 +275,9 @@ int snk_algorithmic_bytes_per_step(const snk_config* cfg, double mean_sum_len, d
 
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 int snk_launch_count(const snk_handle* h, uint64_t* out);
+/* The launch plan of the step kernel (bench.py's config.kernel): kind (0 lane, 1 tile, 2 dense, 3 rows), grid, block,
+ * dynamic shared memory bytes, resident CTAs per SM, envs per CTA. */
+int snk_launch_info(const snk_handle* h, int32_t* out /*[6]*/);
 
 #ifdef __cplusplus
 }

@@ -170,3 +170,39 @@ def gen_actions(cfg, step, seed, n_actions=5):
     a = np.zeros((cfg.num_envs, cfg.n_snakes), dtype=np.int8)
     lib().so_gen_actions(C.byref(cfg), _p(a), C.c_uint64(step), C.c_uint64(seed), C.c_int32(n_actions))
     return a
+
+
+class BlockOracles(object):
+    """C oracles for a few contiguous blocks of a large batch (parity at full size without stepping every env on the
+    CPU): block b covers envs [first_b, first_b + count_b) of a batch whose env 0 has global id `env_id_base`.  RNG and
+    the synthetic action stream are keyed by the GLOBAL env id, so a block oracle started from reset follows exactly the
+    trajectories of those envs inside the big batch.  Blocks step in parallel threads (ctypes drops the GIL)."""
+
+    def __init__(self, blocks, env_id_base=0, **kw):
+        self.blocks = [(int(f), int(c), COracle(int(c), env_id_base=env_id_base + int(f), **kw)) for f, c in blocks]
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=min(len(self.blocks), os.cpu_count() or 1))
+
+    @staticmethod
+    def spread(n_envs, n_blocks, count):
+        """n_blocks blocks of `count` envs: the first, the last (incl. a ragged tail) and evenly spaced ones."""
+        count = min(count, n_envs)
+        if n_blocks <= 1 or count >= n_envs:
+            return [(0, count)]
+        firsts = sorted({int(round(i * (n_envs - count) / float(n_blocks - 1))) for i in range(n_blocks)})
+        return [(f, count) for f in firsts]
+
+    def reset(self):
+        return list(self._pool.map(lambda b: b[2].reset().copy(), self.blocks))
+
+    def step_generated(self, step, seed, n_actions, want_obs=True):
+        """Every block plays the synthetic action stream (so_gen_actions, keyed by global env id)."""
+        def one(b):
+            co = b[2]
+            a = gen_actions(co.cfg, step, seed, n_actions)
+            return co.step(a, want_obs=want_obs)
+        return list(self._pool.map(one, self.blocks))
+
+    def step(self, actions, want_obs=True):
+        """`actions`: int8 [N_big, S] of the whole batch; each block takes its rows."""
+        return list(self._pool.map(lambda b: b[2].step(actions[b[0]:b[0] + b[1]], want_obs=want_obs), self.blocks))

@@ -14,7 +14,9 @@ OBS_NATIVE, OBS_ATARI84 = 0, 1
 RNG_PHILOX, RNG_TAPE = 0, 1
 NSTATS = 8
 STAT_NAMES = ("env_steps", "episodes", "return_sum", "length_sum", "fruits", "deaths", "body_cells", "draws")
-DEVERR = {1: "draw tape underrun", 2: "draw tape bound mismatch", 4: "fruit count overflow", 8: "body ring overflow"}
+DEVERR = {1: "draw tape underrun", 2: "draw tape bound mismatch", 4: "fruit count overflow", 8: "body ring overflow",
+          16: "bad state blob (non-adjacent segments, cell id or length out of range)"}
+GRAPH_SYNC_BACK = 1
 
 
 class SnkConfig(C.Structure):
@@ -28,7 +30,7 @@ class SnkBuffers(C.Structure):
     _fields_ = [("d_obs", C.c_void_p), ("d_reward", C.c_void_p), ("d_reward_all", C.c_void_p), ("d_done", C.c_void_p),
                 ("d_num_alive", C.c_void_p), ("d_episode_return", C.c_void_p), ("d_episode_len", C.c_void_p),
                 ("d_stats", C.c_void_p), ("obs_bytes", C.c_size_t), ("obs_h", C.c_int32), ("obs_w", C.c_int32),
-                ("obs_c", C.c_int32)]
+                ("obs_c", C.c_int32), ("d_info_block", C.c_void_p), ("info_block_bytes", C.c_size_t)]
 
 
 class SnkStateLayout(C.Structure):
@@ -42,21 +44,37 @@ _SIGNATURES = {
     "snk_version": (C.c_int, []),
     "snk_last_error": (C.c_char_p, []),
     "snk_create": (C.c_int, [C.POINTER(SnkConfig), C.POINTER(C.c_void_p)]),
+    "snk_create_ex": (C.c_int, [C.POINTER(SnkConfig), C.c_char_p, C.POINTER(C.c_void_p)]),
     "snk_destroy": (C.c_int, [C.c_void_p]),
     "snk_get_config": (C.c_int, [C.c_void_p, C.POINTER(SnkConfig)]),
     "snk_get_buffers": (C.c_int, [C.c_void_p, C.POINTER(SnkBuffers)]),
     "snk_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snk_step_host_views": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snk_step_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snk_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "snk_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "snk_graph_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                   C.POINTER(C.c_void_p)]),
+    "snk_graph_create_scripted": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "snk_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "snk_graph_destroy": (C.c_int, [C.c_void_p]),
     "snk_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_set_obs_target": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "snk_set_draw_tape": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_state_layout_of": (C.c_int, [C.POINTER(SnkConfig), C.POINTER(SnkStateLayout)]),
     "snk_dump_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "snk_dump_state_range": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t]),
     "snk_load_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "snk_get_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_reset_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "snk_check_errors": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]),
+    "snk_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "snk_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "snk_get_stats_global": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snk_comm_bench": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
+    "snk_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "snk_gen_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
     "snk_gen_scripted_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
     "snk_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_int64,

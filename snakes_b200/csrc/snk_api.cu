@@ -1,10 +1,15 @@
 // snk_api.cu -- the extern "C" boundary of libsnk.so (include/snk.h): handle lifetime, device
 // buffers, launch planning.  No torch, no Python: plain pointers and sizes.
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
+#include <algorithm>
+#include <string>
 #include <vector>
 
 #include "snk_device.cuh"
@@ -26,6 +31,23 @@ static int fail(int code, const char* fmt, ...) {
     if (_e != cudaSuccess) return fail(SNK_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e));    \
   } while (0)
 
+struct snk_graph;
+
+// ---- NCCL, bound at run time (dlopen): libsnk.so has no link-time dependency on it, and inside a PyTorch process the
+// soname resolves to the libnccl.so.2 torch already loaded, so there is one NCCL in the process.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* so;
+  int (*GetUniqueId)(ncclUniqueId*);
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  int (*CommDestroy)(ncclComm_t);
+  int (*AllReduce)(const void*, void*, size_t, int /*ncclDataType_t*/, int /*ncclRedOp_t*/, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(int);
+  int (*GetVersion)(int*);
+};
+static const int kNcclFloat64 = 8, kNcclSum = 0;  // nccl.h: ncclFloat64 = 8, ncclSum = 0 (stable since NCCL 2.0)
+
 struct snk_handle {
   snk_config cfg;
   snk_state_layout lay;
@@ -41,12 +63,59 @@ struct snk_handle {
   uint32_t* d_tape_vals;
   uint32_t* d_tape_bounds;
   uint64_t* d_tape_off;
+  size_t blob_bytes;
+  uint8_t* d_info;        // done | num_alive | fin_ret | fin_len, contiguous (snk_buffers.d_info_block)
+  size_t info_bytes;
+  uint8_t* d_views;       // host-buffer step with fewer views than K: packed staging [N][V][V][3 n]
+  size_t views_bytes;
   std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> host_allocs;  // snk_host_alloc: pinned, NUMA-local
   uint64_t launches;
+  // per-step statistics all-reduce (snk_comm_init)
+  ncclComm_t comm;
+  int comm_ranks, comm_rank;
+  cudaStream_t side;           // high-priority side stream the all-reduce runs on
+  cudaStream_t cap_stream;     // private stream graphs are captured on
+  double* d_snap;              // [2][SNK_NSTATS] per-step snapshots of the local sums (written by the step kernel)
+  double* d_global;            // [2][SNK_NSTATS] their sums over all ranks
+  cudaEvent_t ev_step[2], ev_red[2], cev_step[2], cev_red[2];  // eager / capture-time fork + join events
+  bool ev_red_valid[2];
+  uint64_t step_seq;           // steps launched so far: slot = step_seq & 1
+  uint64_t collectives;
+  int last_slot;
+  snk_graph* rollout_cache;    // the graph of the last snk_rollout call (re-launched when the arguments repeat)
+  std::string debug;
 };
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 static int gcd(int a, int b) { return b ? gcd(b, a % b) : a; }
+
+// ---- experiment switches.  ONE string of comma-separated key=value pairs, given explicitly to snk_create_ex or, for
+// snk_create, read from the single environment variable SNK_DEBUG.  None changes results (all are parity-tested); an
+// unset / empty string is the production configuration.  Keys: force_kernel=lane|tile|rows|dense, lane=fused|ws|split,
+// store=stg, l2=<bits>, pdl=0, restore_thr=<n>, logic_warps=<n>, rows_kb=<n>, rows_block=<n>, extra_smem=<bytes>.
+static bool dbg_get(const std::string& opts, const char* key, std::string* out) {
+  size_t pos = 0;
+  const size_t klen = strlen(key);
+  while (pos < opts.size()) {
+    size_t end = opts.find_first_of(", ;", pos);
+    if (end == std::string::npos) end = opts.size();
+    if (end - pos > klen && opts.compare(pos, klen, key) == 0 && opts[pos + klen] == '=') {
+      *out = opts.substr(pos + klen + 1, end - pos - klen - 1);
+      return true;
+    }
+    pos = end + 1;
+  }
+  return false;
+}
+static int dbg_int(const std::string& opts, const char* key, int dflt) {
+  std::string v;
+  return dbg_get(opts, key, &v) ? atoi(v.c_str()) : dflt;
+}
+static bool dbg_is(const std::string& opts, const char* key, const char* value) {
+  std::string v;
+  return dbg_get(opts, key, &v) && v == value;
+}
 
 static int cfg_check(const snk_config* c) {
   if (!c) return fail(SNK_EINVAL, "config is NULL");
@@ -63,7 +132,8 @@ static int cfg_check(const snk_config* c) {
   if (c->obs_mode == SNK_OBS_ATARI84 && (c->n_views ? c->n_views : c->n_snakes) > 8)
     return fail(SNK_EINVAL, "obs_mode atari84 supports at most 8 views");
   if (c->rng_mode != SNK_RNG_PHILOX && c->rng_mode != SNK_RNG_TAPE) return fail(SNK_EINVAL, "unknown rng_mode %d", c->rng_mode);
-  if ((uint64_t)(c->env_id_base + c->num_envs) > 0xffffffffull) return fail(SNK_EINVAL, "global env ids must fit 32 bits");
+  if (c->env_id_base < 0) return fail(SNK_EINVAL, "env_id_base must be >= 0");
+  if ((uint64_t)c->env_id_base + (uint64_t)c->num_envs > 0xffffffffull) return fail(SNK_EINVAL, "global env ids must fit 32 bits");
   return SNK_OK;
 }
 
@@ -106,11 +176,75 @@ static int dev_alloc(snk_handle* h, T** out, size_t count, bool zero) {
   return SNK_OK;
 }
 
+static void dev_free(snk_handle* h, void* ptr) {
+  if (!ptr) return;
+  auto it = std::find(h->allocs.begin(), h->allocs.end(), ptr);
+  if (it != h->allocs.end()) h->allocs.erase(it);
+  cudaFree(ptr);
+}
+
+// ------------------------------------------------------------------ NCCL binding
+static NcclApi g_nccl = {};
+static int nccl_load() {
+  if (g_nccl.so) return SNK_OK;
+  void* so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!so) so = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!so) return fail(SNK_ECOMM, "libnccl.so.2 not found: %s", dlerror());
+  NcclApi a = {};
+  a.so = so;
+  *(void**)&a.GetUniqueId = dlsym(so, "ncclGetUniqueId");
+  *(void**)&a.CommInitRank = dlsym(so, "ncclCommInitRank");
+  *(void**)&a.CommDestroy = dlsym(so, "ncclCommDestroy");
+  *(void**)&a.AllReduce = dlsym(so, "ncclAllReduce");
+  *(void**)&a.GetErrorString = dlsym(so, "ncclGetErrorString");
+  *(void**)&a.GetVersion = dlsym(so, "ncclGetVersion");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.GetErrorString)
+    return fail(SNK_ECOMM, "libnccl.so.2 lacks a required symbol");
+  g_nccl = a;
+  return SNK_OK;
+}
+#define NCCL_TRY(expr)                                                                            \
+  do {                                                                                            \
+    int _r = (expr);                                                                              \
+    if (_r != 0) return fail(SNK_ECOMM, "%s: %s", #expr, g_nccl.GetErrorString(_r));             \
+  } while (0)
+
+struct snk_graph {
+  snk_handle* h;
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  int T;
+  uint64_t launches_per_run, collectives_per_run;
+  // arguments it was captured with (snk_rollout's cache key)
+  const int8_t* d_actions; int32_t n_batches; uint8_t* d_obs; float* d_reward; uint8_t* d_done; uint32_t flags;
+  uint8_t* obs_target; bool with_comm;
+};
+
+extern "C" int snk_graph_destroy(snk_graph* g) {
+  if (!g) return SNK_OK;
+  if (g->h && g->h->rollout_cache == g) g->h->rollout_cache = nullptr;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+  return SNK_OK;
+}
+
 extern "C" int snk_destroy(snk_handle* h) {
   if (!h) return SNK_OK;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
+  if (h->rollout_cache) snk_graph_destroy(h->rollout_cache);
+  if (h->comm && g_nccl.so) g_nccl.CommDestroy(h->comm);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_step[i]) cudaEventDestroy(h->ev_step[i]);
+    if (h->ev_red[i]) cudaEventDestroy(h->ev_red[i]);
+    if (h->cev_step[i]) cudaEventDestroy(h->cev_step[i]);
+    if (h->cev_red[i]) cudaEventDestroy(h->cev_red[i]);
+  }
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (void* q : h->allocs) cudaFree(q);
+  for (auto& q : h->host_allocs) cudaFreeHost(q.first);
   delete h;
   return SNK_OK;
 }
@@ -122,7 +256,7 @@ extern "C" int snk_destroy(snk_handle* h) {
     if (_e != cudaSuccess) { snk_destroy(h); return fail(SNK_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); } \
   } while (0)
 
-extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
+extern "C" int snk_create_ex(const snk_config* cfg, const char* debug_opts, snk_handle** out) {
   int rc = cfg_check(cfg);
   if (rc) return rc;
   if (!out) return fail(SNK_EINVAL, "out is NULL");
@@ -135,8 +269,13 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   if (h->cfg.n_views == 0) h->cfg.n_views = cfg->n_snakes;
   if (h->cfg.max_steps == 0) h->cfg.max_steps = 2000;
   h->launches = 0;
-  h->d_obs_own = nullptr; h->d_actions_own = nullptr; h->d_blob = nullptr;
+  h->d_obs_own = nullptr; h->d_actions_own = nullptr; h->d_blob = nullptr; h->blob_bytes = 0; h->d_views = nullptr; h->views_bytes = 0;
   h->d_tape_vals = h->d_tape_bounds = nullptr; h->d_tape_off = nullptr;
+  h->comm = nullptr; h->comm_ranks = 1; h->comm_rank = 0; h->side = nullptr; h->cap_stream = nullptr;
+  h->d_snap = h->d_global = nullptr; h->step_seq = 0; h->collectives = 0; h->last_slot = 0; h->rollout_cache = nullptr;
+  for (int i = 0; i < 2; ++i) { h->ev_step[i] = h->ev_red[i] = h->cev_step[i] = h->cev_red[i] = nullptr; h->ev_red_valid[i] = false; }
+  h->debug = debug_opts ? debug_opts : "";
+  const std::string& dbg = h->debug;
   snk_state_layout_of(&h->cfg, &h->lay);
   cudaDeviceProp prop;
   CUDA_TRY_H(cudaGetDeviceProperties(&prop, cfg->device));
@@ -159,9 +298,10 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
 
   // launch plan.  lane kernel (chain-coded bodies, lane per env) for small boards; otherwise the
   // warp-per-env tile kernel while W observations + template + scratch leave room for >= 2 CTAs per
-  // SM; otherwise the CTA-per-env dense kernel.
+  // SM; otherwise the CTA-per-env rows / dense kernel.
   LaunchPlan& plan = h->plan;
-  const char* force = getenv("SNK_FORCE_KERNEL");  // "lane" | "tile" | "dense": testing aid
+  std::string force;
+  dbg_get(dbg, "force_kernel", &force);
   int TE = 0;
   if (snk_lane_supported(S, K) && F <= 4 && D <= 32) {
     const int cand[3] = {32, 16, 8};
@@ -177,29 +317,29 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     const int unit = 16 / gcd(V * p.C, 16);
     // chunk size and CTA shape measured on B200 at 16 snakes on 64x64: 4 warps (1 producer + 3 consumers) give 7 CTAs
     // per SM, and 8 KB chunks beat 12 KB (32 768 envs: classic 1280 us, cut 1502 vs 1551 us)
-    { const char* rk = getenv("SNK_ROWS_KB"); const size_t lim = (size_t)(rk ? atoi(rk) : 8) * 1024;
-      for (int r = unit; r <= V && ((size_t)r * V * p.C <= lim || !R); r += unit) { if ((size_t)r * V * p.C > 48 * 1024) break; R = r; } }
+    const size_t lim = (size_t)dbg_int(dbg, "rows_kb", 8) * 1024;
+    for (int r = unit; r <= V && ((size_t)r * V * p.C <= lim || !R); r += unit) { if ((size_t)r * V * p.C > 48 * 1024) break; R = r; }
   }
   plan.kind = TE ? KIND_LANE : smem_tile <= 110 * 1024 ? KIND_TILE : R ? KIND_ROWS : KIND_DENSE;
-  if (force && !strcmp(force, "dense")) plan.kind = KIND_DENSE;
-  if (force && !strcmp(force, "rows")) {
+  if (force == "dense") plan.kind = KIND_DENSE;
+  if (force == "rows") {
     if (!R) { snk_destroy(h); return fail(SNK_EINVAL, "rows kernel does not support this configuration"); }
     plan.kind = KIND_ROWS;
   }
-  if (force && !strcmp(force, "tile") && smem_tile <= 200 * 1024) plan.kind = KIND_TILE;
-  if (force && !strcmp(force, "lane") && !TE) { snk_destroy(h); return fail(SNK_EINVAL, "lane kernel does not support this configuration"); }
+  if (force == "tile" && smem_tile <= 200 * 1024) plan.kind = KIND_TILE;
+  if (force == "lane" && !TE) { snk_destroy(h); return fail(SNK_EINVAL, "lane kernel does not support this configuration"); }
   p.family = plan.kind == KIND_LANE;
-  { const char* sm = getenv("SNK_STORE"); p.store_mode = (sm && !strcmp(sm, "stg")) ? 1 : 0; }
-  {  // L2 policies (SNK_L2 = bit0 obs evict-first, bit1 records evict-last; testing aid)
-    const char* l2 = getenv("SNK_L2");
-    const int bits = l2 ? atoi(l2) : 3;
+  p.store_mode = dbg_is(dbg, "store", "stg") ? 1 : 0;
+  {  // L2 policies (l2 = bit0 obs evict-first, bit1 records evict-last)
+    const int bits = dbg_int(dbg, "l2", 3);
     p.obs_evict_first = bits & 1; p.rec_evict_last = (bits >> 1) & 1;
   }
   int logic_warps = 3;
-  // lane path variants (SNK_LANE=fused|ws|split, testing aid): every warp steps 32 envs then streams
-  // their images (default: fastest measured), warp-specialised single kernel, or two kernels
+  // lane path variants (lane=fused|ws|split): every warp steps 32 envs then streams their images (default: fastest
+  // measured), warp-specialised single kernel, or two kernels
   {
-    const char* lv = getenv("SNK_LANE");
+    std::string lv;
+    const bool have_lv = dbg_get(dbg, "lane", &lv);
     // measured on B200: with a small image per env (3 views of 12x12: 1296 B) the step is bound by the
     // logic's latency and the warp-specialised form (more logic warps per image buffer) is 1.4x faster;
     // with 2646 B per env (2 views of 21x21) the image stream dominates and the fused form wins
@@ -211,13 +351,11 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
     // fastest small-image form (65 536 envs, 10x10: 3 snakes cut 53.0 vs 61.3 us, 3 snakes classic 44.0 vs 48.8,
     // 2 snakes 34.6 vs 38.8; 1 M envs cut 648 vs 751 us); a single snake stays warp-specialised (23.6 vs 29.2 us).
     const bool small_image = p.E < 2048 && (N + 31) / 32 >= 2LL * h->n_sm;
-    plan.ws = plan.kind == KIND_LANE && (lv ? !strcmp(lv, "ws") : (small_image && S == 1));
-    plan.split = plan.kind == KIND_LANE && (lv ? !strcmp(lv, "split") : (small_image && S > 1));
-    { const char* pd = getenv("SNK_PDL"); plan.pdl = !(pd && !strcmp(pd, "0")); }
-
-    const char* lw = getenv("SNK_LOGIC_WARPS");
+    plan.ws = plan.kind == KIND_LANE && (have_lv ? lv == "ws" : (small_image && S == 1));
+    plan.split = plan.kind == KIND_LANE && (have_lv ? lv == "split" : (small_image && S > 1));
+    plan.pdl = dbg_int(dbg, "pdl", 1) != 0;
     p.PW = 2;
-    logic_warps = lw ? atoi(lw) : 3;
+    logic_warps = dbg_int(dbg, "logic_warps", 3);
     if (logic_warps < 1 || logic_warps > 3) logic_warps = 3;
   }
   p.CW = (p.cap - 1 + 15) / 16;
@@ -229,23 +367,20 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
        // the restore costs one 16-byte store per 512 bytes of image plus the border units of one env spread over its
        // LPE lanes; a walked segment costs about 16 instructions.  Measured on B200 (2x19x19, 131072 envs, fruit-seeking
        // policy, sum of lengths 22): thresholds 3 / 5 / 8 / 12 -> 145.9 / 145.1 / 146.8 / 152.9 us, always-walk 161.1 us;
-       // random actions (sum of lengths 4.4) unchanged.  SNK_RESTORE_THR overrides (0 = always walk).
+       // random actions (sum of lengths 4.4) unchanged.  restore_thr overrides (0 = always walk).
       const int U = (p.C & 1) ? 1 : 2, LPE = 32 / TE;
       const int border_units = (2 * (V * p.C + p.C) + (V - 3) * 2 * p.C) / U;
       const int stores = (int)((size_t)TE * p.E / 512) + border_units / LPE;
-      p.restore_thr = stores / 16 < 3 ? 3 : stores / 16;
-      const char* rt = getenv("SNK_RESTORE_THR");
-      if (rt) p.restore_thr = atoi(rt);
+      p.restore_thr = dbg_int(dbg, "restore_thr", stores / 16 < 3 ? 3 : stores / 16);
     }
     plan.block = plan.ws ? 32 * (p.PW + logic_warps) : 64;
-    plan.smem = (size_t)2 * p.tile_stride;
-    { const char* xs = getenv("SNK_EXTRA_SMEM"); if (xs) plan.smem += (size_t)atoi(xs); }  // experiment: fewer resident CTAs (image buffers) per SM
+    plan.smem = (size_t)2 * p.tile_stride + (size_t)dbg_int(dbg, "extra_smem", 0);  // extra_smem: fewer resident image buffers per SM (experiment)
     p.n_groups = (N + 31) / 32;
   } else if (plan.kind == KIND_TILE) {
     p.W = W; plan.block = 32 * W; plan.smem = smem_tile;
     p.n_groups = (N + W - 1) / W;
   } else if (plan.kind == KIND_ROWS) {
-    p.W = 1; p.R = R; { const char* rb = getenv("SNK_ROWS_BLOCK"); plan.block = rb ? atoi(rb) : 128; }  // 1 producer warp + 3 consumer warps
+    p.W = 1; p.R = R; plan.block = dbg_int(dbg, "rows_block", 128);  // 1 producer warp + 3 consumer warps
     p.tile_stride = (int)(((size_t)R * V * p.C + 127) & ~(size_t)127);
     plan.smem = 2 * (((size_t)p.VV + 127) & ~(size_t)127) + 2 * (size_t)p.tile_stride + (size_t)(p.RW + p.bm_words) * 4;
     p.n_groups = N;
@@ -282,12 +417,18 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   }
   TRY(dev_alloc(h, &p.reward, (size_t)N, true));
   TRY(dev_alloc(h, &p.reward_all, (size_t)N * S, true));
-  TRY(dev_alloc(h, &p.done, (size_t)N, true));
-  TRY(dev_alloc(h, &p.num_alive, (size_t)N, true));
-  TRY(dev_alloc(h, &p.fin_ret, (size_t)N, true));
-  TRY(dev_alloc(h, &p.fin_len, (size_t)N, true));
+  {  // done | num_alive | episode return | episode length in ONE block: a caller that must keep a step's infos past the
+     // next step snapshots them with a single copy
+    const size_t nb = align16((size_t)N);
+    h->info_bytes = 2 * nb + 2 * align16(4 * (size_t)N);
+    TRY(dev_alloc(h, &h->d_info, h->info_bytes, true));
+    p.done = h->d_info; p.num_alive = h->d_info + nb;
+    p.fin_ret = reinterpret_cast<float*>(h->d_info + 2 * nb);
+    p.fin_len = reinterpret_cast<int32_t*>(h->d_info + 2 * nb + align16(4 * (size_t)N));
+  }
   TRY(dev_alloc(h, &p.stats, (size_t)SNK_NSTATS, true));
   TRY(dev_alloc(h, &p.err, (size_t)1, true));
+  TRY(dev_alloc(h, &p.ticket, (size_t)1, true));
   TRY(dev_alloc(h, &h->d_actions_own, (size_t)N * S, true));
 
   // lookup tables: padded id -> (outside?, y-major board index incl. the reference's aliasing), and back
@@ -319,10 +460,13 @@ extern "C" int snk_create(const snk_config* cfg, snk_handle** out) {
   TRY(dev_alloc(h, &d_tmpl, tmpl.size(), false));
   CUDA_TRY_H(cudaMemcpy(d_tmpl, tmpl.data(), tmpl.size(), cudaMemcpyHostToDevice));
   p.tmpl = d_tmpl;
+  CUDA_TRY_H(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
   CUDA_TRY_H(cudaDeviceSynchronize());
   *out = h;
   return SNK_OK;
 }
+
+extern "C" int snk_create(const snk_config* cfg, snk_handle** out) { return snk_create_ex(cfg, getenv("SNK_DEBUG"), out); }
 
 extern "C" int snk_get_config(const snk_handle* h, snk_config* out) {
   if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
@@ -336,36 +480,68 @@ extern "C" int snk_get_buffers(const snk_handle* h, snk_buffers* out) {
   out->d_obs = h->d_obs_user; out->d_reward = p.reward; out->d_reward_all = p.reward_all; out->d_done = p.done;
   out->d_num_alive = p.num_alive; out->d_episode_return = p.fin_ret; out->d_episode_len = p.fin_len;
   const int side = h->cfg.obs_mode == SNK_OBS_ATARI84 ? 84 : p.V;
+  out->d_info_block = h->d_info; out->info_block_bytes = h->info_bytes;
   out->d_stats = p.stats; out->obs_bytes = (size_t)p.N * h->obs_out_env_bytes; out->obs_h = side; out->obs_w = side; out->obs_c = p.C;
   return SNK_OK;
 }
 
-struct RolloutSlot {  // per-step output redirection of snk_rollout
+struct RolloutSlot {  // per-step output redirection of a rollout graph
   uint8_t* obs;
   float* reward;
   uint8_t* done;
 };
 
+// One step (or reset / re-encode) on `stream`.  `capturing`: the call is being recorded into a CUDA graph (snk_graph_create);
+// the per-step statistics all-reduce then forks onto the side stream with capture-time events.
 static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_t* d_mask, cudaStream_t stream,
-                  const RolloutSlot* slot = nullptr) {
+                  const RolloutSlot* slot = nullptr, bool capturing = false, int cap_step = 0) {
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   Params p = h->p;
   uint8_t* obs_user = h->d_obs_user;
   if (slot) {
     if (slot->reward) p.reward = slot->reward;
     if (slot->done) p.done = slot->done;
-    obs_user = slot->obs;
-    if (h->cfg.obs_mode != SNK_OBS_ATARI84) p.obs = slot->obs;
+    if (slot->obs) {
+      obs_user = slot->obs;
+      if (h->cfg.obs_mode != SNK_OBS_ATARI84) p.obs = slot->obs;
+    }
   }
   p.mode = mode; p.actions = d_actions; p.mask = d_mask;
   p.tape_vals = h->d_tape_vals; p.tape_bounds = h->d_tape_bounds; p.tape_off = h->d_tape_off;
   if (p.rng_mode == SNK_RNG_TAPE && !p.tape_vals) return fail(SNK_EINVAL, "rng_mode is TAPE but no tape was set");
+  const bool reduce = h->comm && mode == MODE_STEP;
+  int sl = 0;
+  if (reduce) {
+    sl = capturing ? (cap_step & 1) : (int)(h->step_seq & 1);
+    p.snap = h->d_snap + sl * SNK_NSTATS;
+    // the all-reduce that last read this snapshot slot (two steps ago) must be done before the kernel rewrites it
+    if (capturing) { if (cap_step >= 2) CUDA_TRY(cudaStreamWaitEvent(stream, h->cev_red[sl], 0)); }
+    else if (h->ev_red_valid[sl]) CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_red[sl], 0));
+  } else {
+    p.snap = nullptr;
+  }
   CUDA_TRY(snk_launch_step(p, h->cfg.rules, h->plan, stream));
   h->launches += (h->plan.split && mode != MODE_OBSERVE) ? 2 : 1;
+  if (reduce) {
+    // side stream: all-reduce this step's snapshot while the next step runs; its result is read one step late
+    cudaEvent_t es = capturing ? h->cev_step[sl] : h->ev_step[sl], er = capturing ? h->cev_red[sl] : h->ev_red[sl];
+    CUDA_TRY(cudaEventRecord(es, stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->side, es, 0));
+    NCCL_TRY(g_nccl.AllReduce(h->d_snap + sl * SNK_NSTATS, h->d_global + sl * SNK_NSTATS, SNK_NSTATS, kNcclFloat64, kNcclSum, h->comm, h->side));
+    CUDA_TRY(cudaEventRecord(er, h->side));
+    if (!capturing) { h->ev_red_valid[sl] = true; h->step_seq++; h->collectives++; h->last_slot = sl; }
+  }
   if (h->cfg.obs_mode == SNK_OBS_ATARI84) {
     CUDA_TRY(snk_launch_upscale84(p.obs, obs_user, p.N, p.V, p.C, h->n_sm, stream));
     h->launches++;
   }
+  return SNK_OK;
+}
+
+// before work that is not ordered behind the side stream by events of its own (graph launches, stats read-back)
+static int join_side(snk_handle* h, cudaStream_t stream) {
+  for (int i = 0; i < 2; ++i)
+    if (h->ev_red_valid[i]) CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_red[i], 0));
   return SNK_OK;
 }
 
@@ -379,46 +555,220 @@ extern "C" int snk_step(snk_handle* h, const int8_t* d_actions, void* stream) {
   return launch(h, MODE_STEP, d_actions, nullptr, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ CUDA graphs: T steps, one launch
+struct ScriptedArgs { uint64_t step0, seed; int eps_permille; };
+
+static int graph_create_impl(snk_handle* h, const int8_t* d_actions, int32_t n_batches, int32_t T, uint8_t* d_obs,
+                             float* d_reward, uint8_t* d_done, uint32_t flags, const ScriptedArgs* scripted, snk_graph** out) {
+  if (!h || !d_actions || !out || T < 1 || n_batches < 1) return fail(SNK_EINVAL, "bad argument");
+  const Params& p = h->p;
+  const size_t obs_step = (size_t)p.N * h->obs_out_env_bytes;
+  if (d_obs) {
+    if (((uintptr_t)d_obs & 15) != 0) return fail(SNK_EINVAL, "rollout obs buffer must be 16-byte aligned");
+    if (obs_step % 16 != 0 && T > 1) return fail(SNK_EINVAL, "N * obs bytes per env must be a multiple of 16 for a rollout");
+  }
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  snk_graph* g = new snk_graph();
+  g->h = h; g->graph = nullptr; g->exec = nullptr; g->T = T;
+  g->d_actions = d_actions; g->n_batches = n_batches; g->d_obs = d_obs; g->d_reward = d_reward; g->d_done = d_done; g->flags = flags;
+  g->obs_target = h->d_obs_user; g->with_comm = h->comm != nullptr;
+  const uint64_t l0 = h->launches;
+  cudaStream_t s = h->cap_stream;
+  cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+  if (ce != cudaSuccess) { delete g; return fail(SNK_ECUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(ce)); }
+  int rc = SNK_OK;
+  for (int32_t t = 0; t < T && rc == SNK_OK; ++t) {
+    RolloutSlot slot;
+    slot.obs = d_obs ? d_obs + (size_t)t * obs_step : nullptr;
+    slot.reward = d_reward ? d_reward + (size_t)t * p.N : nullptr;
+    slot.done = d_done ? d_done + (size_t)t * p.N : nullptr;
+    if (scripted) {  // the policy kernel reads the state step t-1 left and writes this step's actions
+      if (snk_launch_scripted_actions(h->p, h->d_actions_own, scripted->step0 + (uint64_t)t, scripted->seed, scripted->eps_permille, s) != cudaSuccess)
+        rc = fail(SNK_ECUDA, "capture: scripted policy kernel");
+      h->launches++;
+    }
+    if (rc == SNK_OK) rc = launch(h, MODE_STEP, d_actions + (size_t)(t % n_batches) * p.N * p.S, nullptr, s, &slot, true, t);
+  }
+  if (rc == SNK_OK && h->comm) {  // join the side stream's last two all-reduces back into the origin stream
+    for (int t = T - 2 < 0 ? 0 : T - 2; t < T; ++t)
+      if (cudaStreamWaitEvent(s, h->cev_red[t & 1], 0) != cudaSuccess) rc = fail(SNK_ECUDA, "cudaStreamWaitEvent (capture join)");
+  }
+  if (rc == SNK_OK && d_obs && (flags & SNK_GRAPH_SYNC_BACK)) {
+    // leave the handle's own buffers as after T calls of snk_step
+    const uint8_t* last = d_obs + (size_t)(T - 1) * obs_step;
+    if (cudaMemcpyAsync(h->d_obs_user, last, obs_step, cudaMemcpyDeviceToDevice, s) != cudaSuccess) rc = fail(SNK_ECUDA, "capture: obs copy-back");
+    if (d_reward && cudaMemcpyAsync(p.reward, d_reward + (size_t)(T - 1) * p.N, (size_t)p.N * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      rc = fail(SNK_ECUDA, "capture: reward copy-back");
+    if (d_done && cudaMemcpyAsync(p.done, d_done + (size_t)(T - 1) * p.N, (size_t)p.N, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      rc = fail(SNK_ECUDA, "capture: done copy-back");
+  }
+  ce = cudaStreamEndCapture(s, &g->graph);
+  g->launches_per_run = h->launches - l0;
+  h->launches = l0;  // nothing ran yet
+  g->collectives_per_run = h->comm ? (uint64_t)T : 0;
+  if (rc != SNK_OK) { snk_graph_destroy(g); return rc; }
+  if (ce != cudaSuccess) { snk_graph_destroy(g); return fail(SNK_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce)); }
+  ce = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (ce != cudaSuccess) { snk_graph_destroy(g); return fail(SNK_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+  *out = g;
+  return SNK_OK;
+}
+
+extern "C" int snk_graph_create(snk_handle* h, const int8_t* d_actions, int32_t n_batches, int32_t T, uint8_t* d_obs,
+                                float* d_reward, uint8_t* d_done, uint32_t flags, snk_graph** out) {
+  return graph_create_impl(h, d_actions, n_batches, T, d_obs, d_reward, d_done, flags, nullptr, out);
+}
+
+extern "C" int snk_graph_create_scripted(snk_handle* h, int32_t T, uint64_t step0, uint64_t seed, int32_t eps_permille, snk_graph** out) {
+  if (!h || eps_permille < 0 || eps_permille > 1000) return fail(SNK_EINVAL, "bad argument");
+  if (h->p.family != 1 || h->cfg.rules != SNK_RULES_CLASSIC)
+    return fail(SNK_EINVAL, "the scripted policy needs a lane-family configuration with classic rules");
+  ScriptedArgs a = {step0, seed, eps_permille};
+  return graph_create_impl(h, h->d_actions_own, 1, T, nullptr, nullptr, nullptr, 0, &a, out);
+}
+
+extern "C" int snk_graph_launch(snk_graph* g, void* stream) {
+  if (!g || !g->exec) return fail(SNK_EINVAL, "graph is NULL");
+  snk_handle* h = g->h;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (g->with_comm) {
+    int rc = join_side(h, s);  // eager all-reduces still reading the snapshot slots
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaGraphLaunch(g->exec, s));
+  h->launches += g->launches_per_run;
+  if (g->with_comm) {
+    h->collectives += g->collectives_per_run;
+    h->last_slot = (g->T - 1) & 1;
+    h->step_seq = (uint64_t)g->T;  // the next eager step continues the slot alternation
+    h->ev_red_valid[0] = h->ev_red_valid[1] = false;  // the graph joined its own all-reduces; stream order covers them
+  }
+  return SNK_OK;
+}
+
 extern "C" int snk_rollout(snk_handle* h, const int8_t* d_actions, int32_t T, uint8_t* d_obs, float* d_reward, uint8_t* d_done,
                            void* stream) {
   if (!h || !d_actions || !d_obs || T < 1) return fail(SNK_EINVAL, "bad argument");
-  if (((uintptr_t)d_obs & 15) != 0) return fail(SNK_EINVAL, "rollout obs buffer must be 16-byte aligned");
-  const Params& p = h->p;
-  const size_t obs_step = (size_t)p.N * h->obs_out_env_bytes;
-  if (obs_step % 16 != 0 && T > 1) return fail(SNK_EINVAL, "N * obs bytes per env must be a multiple of 16 for a rollout");
-  cudaStream_t s = (cudaStream_t)stream;
-  for (int32_t t = 0; t < T; ++t) {
-    RolloutSlot slot;
-    slot.obs = d_obs + (size_t)t * obs_step;
-    slot.reward = d_reward ? d_reward + (size_t)t * p.N : nullptr;
-    slot.done = d_done ? d_done + (size_t)t * p.N : nullptr;
-    int rc = launch(h, MODE_STEP, d_actions + (size_t)t * p.N * p.S, nullptr, s, &slot);
-    if (rc) return rc;
+  snk_graph* g = h->rollout_cache;
+  const uint32_t flags = SNK_GRAPH_SYNC_BACK;
+  if (g && !(g->d_actions == d_actions && g->n_batches == T && g->T == T && g->d_obs == d_obs && g->d_reward == d_reward &&
+             g->d_done == d_done && g->flags == flags && g->obs_target == h->d_obs_user && g->with_comm == (h->comm != nullptr))) {
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));  // the cached graph may still be running
+    snk_graph_destroy(g);
+    g = nullptr;
   }
-  // leave the handle's own buffers as after T calls of snk_step
-  RolloutSlot last;
-  last.obs = d_obs + (size_t)(T - 1) * obs_step;
-  CUDA_TRY(cudaMemcpyAsync(h->d_obs_user, last.obs, obs_step, cudaMemcpyDeviceToDevice, s));
-  if (d_reward) CUDA_TRY(cudaMemcpyAsync(p.reward, d_reward + (size_t)(T - 1) * p.N, (size_t)p.N * 4, cudaMemcpyDeviceToDevice, s));
-  if (d_done) CUDA_TRY(cudaMemcpyAsync(p.done, d_done + (size_t)(T - 1) * p.N, (size_t)p.N, cudaMemcpyDeviceToDevice, s));
+  if (!g) {
+    int rc = snk_graph_create(h, d_actions, T, T, d_obs, d_reward, d_done, flags, &g);
+    if (rc) return rc;
+    h->rollout_cache = g;
+  }
+  return snk_graph_launch(g, stream);
+}
+
+// ------------------------------------------------------------------ host-buffer step
+static int step_host_impl(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, int32_t n_views_out, float* h_reward,
+                          uint8_t* h_done, uint8_t* h_num_alive, void* stream, bool sync) {
+  if (!h || !h_actions) return fail(SNK_EINVAL, "NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const Params& p = h->p;
+  if (n_views_out <= 0 || n_views_out > p.K) n_views_out = p.K;
+  if (n_views_out < p.K && n_views_out > 4) return fail(SNK_EINVAL, "a view subset holds at most 4 views");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpyAsync(h->d_actions_own, h_actions, (size_t)p.N * p.S, cudaMemcpyHostToDevice, s));
+  int rc = launch(h, MODE_STEP, h->d_actions_own, nullptr, s);
+  if (rc) return rc;
+  // the small arrays first: the learner's bookkeeping can start while the observations are still in flight
+  if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, p.reward, (size_t)p.N * 4, cudaMemcpyDeviceToHost, s));
+  if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, p.done, (size_t)p.N, cudaMemcpyDeviceToHost, s));
+  if (h_num_alive) CUDA_TRY(cudaMemcpyAsync(h_num_alive, p.num_alive, (size_t)p.N, cudaMemcpyDeviceToHost, s));
+  if (h_obs) {
+    const size_t px_per_env = h->obs_out_env_bytes / (size_t)p.C;
+    if (n_views_out == p.K) {
+      CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs_user, (size_t)p.N * h->obs_out_env_bytes, cudaMemcpyDeviceToHost, s));
+    } else {
+      const size_t bytes = (size_t)p.N * px_per_env * 3 * (size_t)n_views_out;
+      if (h->views_bytes < bytes) {
+        dev_free(h, h->d_views); h->d_views = nullptr; h->views_bytes = 0;
+        if ((rc = dev_alloc(h, &h->d_views, bytes, false))) return rc;
+        h->views_bytes = bytes;
+      }
+      CUDA_TRY(snk_launch_extract_views(h->d_obs_user, h->d_views, (long long)((size_t)p.N * px_per_env), p.C, n_views_out, s));
+      h->launches++;
+      CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_views, bytes, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  if (sync) CUDA_TRY(cudaStreamSynchronize(s));
   return SNK_OK;
 }
 
 extern "C" int snk_step_host(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, float* h_reward, uint8_t* h_done,
                              uint8_t* h_num_alive, void* stream) {
-  if (!h || !h_actions) return fail(SNK_EINVAL, "NULL argument");
-  cudaStream_t s = (cudaStream_t)stream;
-  const Params& p = h->p;
+  return step_host_impl(h, h_actions, h_obs, 0, h_reward, h_done, h_num_alive, stream, true);
+}
+
+extern "C" int snk_step_host_views(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, int32_t n_views_out, float* h_reward,
+                                   uint8_t* h_done, uint8_t* h_num_alive, void* stream) {
+  return step_host_impl(h, h_actions, h_obs, n_views_out, h_reward, h_done, h_num_alive, stream, true);
+}
+
+extern "C" int snk_step_host_async(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, int32_t n_views_out, float* h_reward,
+                                   uint8_t* h_done, uint8_t* h_num_alive, void* stream) {
+  return step_host_impl(h, h_actions, h_obs, n_views_out, h_reward, h_done, h_num_alive, stream, false);
+}
+
+// Pinned host memory on the NUMA node the handle's GPU hangs off: with one process per GPU all writing ~350 MB of
+// observations per step into host DRAM, buffers that land on one socket (first touch by whichever core ran the
+// allocation) make seven of eight GPUs cross the inter-socket link.  The node comes from sysfs; the pages are placed by
+// a temporary MPOL_BIND memory policy around cudaHostAlloc (raw syscall, no libnuma).
+static int gpu_numa_node(int device) {
+  char bus[32] = "";
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return -1;
+  for (char* c = bus; *c; ++c) if (*c >= 'A' && *c <= 'Z') *c += 'a' - 'A';
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+
+extern "C" int snk_host_alloc(snk_handle* h, size_t bytes, void** out, int32_t* numa_node) {
+  if (!h || !out || !bytes) return fail(SNK_EINVAL, "bad argument");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(cudaMemcpyAsync(h->d_actions_own, h_actions, (size_t)p.N * p.S, cudaMemcpyHostToDevice, s));
-  int rc = launch(h, MODE_STEP, h->d_actions_own, nullptr, s);
-  if (rc) return rc;
-  if (h_reward) CUDA_TRY(cudaMemcpyAsync(h_reward, p.reward, (size_t)p.N * 4, cudaMemcpyDeviceToHost, s));
-  if (h_done) CUDA_TRY(cudaMemcpyAsync(h_done, p.done, (size_t)p.N, cudaMemcpyDeviceToHost, s));
-  if (h_num_alive) CUDA_TRY(cudaMemcpyAsync(h_num_alive, p.num_alive, (size_t)p.N, cudaMemcpyDeviceToHost, s));
-  if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs_user, (size_t)p.N * h->obs_out_env_bytes, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  const int node = gpu_numa_node(h->cfg.device);
+  bool bound = false;
+#ifdef SYS_set_mempolicy
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    bound = syscall(SYS_set_mempolicy, 2 /*MPOL_BIND*/, mask, (unsigned long)(8 * sizeof(mask))) == 0;
+  }
+#endif
+  void* ptr = nullptr;
+  cudaError_t e = cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault);
+  if (e == cudaSuccess) memset(ptr, 0, bytes);  // first touch under the policy
+#ifdef SYS_set_mempolicy
+  if (bound) syscall(SYS_set_mempolicy, 0 /*MPOL_DEFAULT*/, nullptr, 0ul);
+#endif
+  if (e != cudaSuccess) return fail(SNK_ENOMEM, "cudaHostAlloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  h->host_allocs.push_back(std::make_pair(ptr, bytes));
+  *out = ptr;
+  if (numa_node) *numa_node = bound ? node : -1;
   return SNK_OK;
+}
+
+extern "C" int snk_host_free(snk_handle* h, void* ptr) {
+  if (!h || !ptr) return SNK_OK;
+  for (size_t i = 0; i < h->host_allocs.size(); ++i)
+    if (h->host_allocs[i].first == ptr) {
+      cudaFreeHost(ptr);
+      h->host_allocs.erase(h->host_allocs.begin() + (long)i);
+      return SNK_OK;
+    }
+  return fail(SNK_EINVAL, "pointer was not allocated by snk_host_alloc on this handle");
 }
 
 extern "C" int snk_set_obs_target(snk_handle* h, uint8_t* d_obs, size_t bytes) {
@@ -442,50 +792,75 @@ extern "C" int snk_set_draw_tape(snk_handle* h, const uint32_t* h_vals, const ui
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   CUDA_TRY(cudaDeviceSynchronize());
   const size_t N = (size_t)h->p.N, n = (size_t)h_offsets[N];
+  dev_free(h, h->d_tape_vals); dev_free(h, h->d_tape_bounds); dev_free(h, h->d_tape_off);  // a previous tape
+  h->d_tape_vals = h->d_tape_bounds = nullptr; h->d_tape_off = nullptr;
   int rc;
   if ((rc = dev_alloc(h, &h->d_tape_vals, n + 1, false))) return rc;
   if ((rc = dev_alloc(h, &h->d_tape_off, N + 1, false))) return rc;
   CUDA_TRY(cudaMemcpy(h->d_tape_vals, h_vals, n * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(h->d_tape_off, h_offsets, (N + 1) * 8, cudaMemcpyHostToDevice));
-  h->d_tape_bounds = nullptr;
   if (h_bounds) {
     if ((rc = dev_alloc(h, &h->d_tape_bounds, n + 1, false))) return rc;
     CUDA_TRY(cudaMemcpy(h->d_tape_bounds, h_bounds, n * 4, cudaMemcpyHostToDevice));
   }
   h->p.rng_mode = SNK_RNG_TAPE;
+  h->cfg.rng_mode = SNK_RNG_TAPE;
   return SNK_OK;
 }
 
-static int ensure_blob(snk_handle* h) {
-  if (h->d_blob) return SNK_OK;
-  return dev_alloc(h, &h->d_blob, h->lay.total_bytes, true);
+static int ensure_blob(snk_handle* h, size_t bytes) {
+  if (h->d_blob && h->blob_bytes >= bytes) return SNK_OK;
+  dev_free(h, h->d_blob);
+  h->d_blob = nullptr; h->blob_bytes = 0;
+  int rc = dev_alloc(h, &h->d_blob, bytes, true);
+  if (rc == SNK_OK) h->blob_bytes = bytes;
+  return rc;
+}
+
+extern "C" int snk_dump_state_range(snk_handle* h, int64_t first, int64_t count, void* h_dst, size_t bytes) {
+  if (!h || !h_dst) return fail(SNK_EINVAL, "NULL argument");
+  if (first < 0 || count < 1 || first + count > h->p.N) return fail(SNK_EINVAL, "env range [%lld, %lld) outside [0, %lld)",
+                                                                    (long long)first, (long long)(first + count), h->p.N);
+  snk_config sub = h->cfg;
+  sub.num_envs = count; sub.env_id_base = h->cfg.env_id_base + first;
+  snk_state_layout lay;
+  int rc = snk_state_layout_of(&sub, &lay);
+  if (rc) return rc;
+  if (bytes < lay.total_bytes) return fail(SNK_EINVAL, "buffer too small: %zu < %zu", bytes, lay.total_bytes);
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if ((rc = ensure_blob(h, lay.total_bytes))) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemset(h->d_blob, 0, lay.total_bytes));
+  CUDA_TRY(snk_launch_dump(h->p, h->d_blob, lay, first, count, 0));
+  h->launches++;
+  CUDA_TRY(cudaMemcpy(h_dst, h->d_blob, lay.total_bytes, cudaMemcpyDeviceToHost));
+  return SNK_OK;
 }
 
 extern "C" int snk_dump_state(snk_handle* h, void* h_dst, size_t bytes) {
-  if (!h || !h_dst) return fail(SNK_EINVAL, "NULL argument");
-  if (bytes < h->lay.total_bytes) return fail(SNK_EINVAL, "buffer too small: %zu < %zu", bytes, h->lay.total_bytes);
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
-  int rc = ensure_blob(h);
-  if (rc) return rc;
-  CUDA_TRY(cudaDeviceSynchronize());
-  CUDA_TRY(cudaMemset(h->d_blob, 0, h->lay.total_bytes));
-  CUDA_TRY(snk_launch_dump(h->p, h->d_blob, h->lay, 0));
-  h->launches++;
-  CUDA_TRY(cudaMemcpy(h_dst, h->d_blob, h->lay.total_bytes, cudaMemcpyDeviceToHost));
-  return SNK_OK;
+  if (!h) return fail(SNK_EINVAL, "NULL argument");
+  return snk_dump_state_range(h, 0, h->p.N, h_dst, bytes);
 }
 
 extern "C" int snk_load_state(snk_handle* h, const void* h_src, size_t bytes) {
   if (!h || !h_src) return fail(SNK_EINVAL, "NULL argument");
   if (bytes < h->lay.total_bytes) return fail(SNK_EINVAL, "buffer too small: %zu < %zu", bytes, h->lay.total_bytes);
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  int rc = ensure_blob(h);
+  int rc = ensure_blob(h, h->lay.total_bytes);
   if (rc) return rc;
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(h->d_blob, h_src, h->lay.total_bytes, cudaMemcpyHostToDevice));
   CUDA_TRY(snk_launch_load(h->p, h->d_blob, h->lay, 0));
   h->launches++;
   CUDA_TRY(cudaDeviceSynchronize());
+  uint32_t flags = 0;
+  CUDA_TRY(cudaMemcpy(&flags, h->p.err, 4, cudaMemcpyDeviceToHost));
+  if (flags & SNK_DEVERR_BAD_STATE) {
+    flags &= ~SNK_DEVERR_BAD_STATE;
+    CUDA_TRY(cudaMemcpy(h->p.err, &flags, 4, cudaMemcpyHostToDevice));
+    return fail(SNK_ESTATE, "state blob rejected: a body that is too long, leaves the padded grid, has a velocity code above 4 "
+                            "or whose consecutive segments are not adjacent cells (those snakes were left empty)");
+  }
   return SNK_OK;
 }
 
@@ -510,6 +885,87 @@ extern "C" int snk_check_errors(snk_handle* h, uint32_t* flags, void* stream) {
   CUDA_TRY(cudaMemcpyAsync(flags, h->p.err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CUDA_TRY(cudaMemsetAsync(h->p.err, 0, 4, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return SNK_OK;
+}
+
+// ------------------------------------------------------------------ the path's one collective
+extern "C" int snk_comm_unique_id(uint8_t* out128) {
+  if (!out128) return fail(SNK_EINVAL, "NULL argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+  return SNK_OK;
+}
+
+extern "C" int snk_comm_init(snk_handle* h, const uint8_t* id128, int32_t n_ranks, int32_t rank) {
+  if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(SNK_EINVAL, "bad argument");
+  if (h->comm) return fail(SNK_EINVAL, "communicator already initialised");
+  int rc = nccl_load();
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  NCCL_TRY(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+  int lo = 0, hi = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CUDA_TRY(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_red[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->cev_step[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->cev_red[i], cudaEventDisableTiming));
+  }
+  if ((rc = dev_alloc(h, &h->d_snap, (size_t)2 * SNK_NSTATS, true))) return rc;
+  if ((rc = dev_alloc(h, &h->d_global, (size_t)2 * SNK_NSTATS, true))) return rc;
+  // one eager all-reduce now: NCCL sets its connections up on first use, which must not happen inside a stream capture
+  NCCL_TRY(g_nccl.AllReduce(h->d_snap, h->d_global, SNK_NSTATS, kNcclFloat64, kNcclSum, comm, h->side));
+  CUDA_TRY(cudaStreamSynchronize(h->side));
+  h->comm = comm; h->comm_ranks = n_ranks; h->comm_rank = rank;
+  if (h->rollout_cache) snk_graph_destroy(h->rollout_cache);  // captured without the collective
+  return SNK_OK;
+}
+
+extern "C" int snk_get_stats_global(snk_handle* h, double* h_stats, void* stream) {
+  if (!h || !h_stats) return fail(SNK_EINVAL, "NULL argument");
+  if (!h->comm) return snk_get_stats(h, h_stats, stream);  // one shard: the local sums are the global ones
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc = join_side(h, s);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h_stats, h->d_global + h->last_slot * SNK_NSTATS, sizeof(double) * SNK_NSTATS, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return SNK_OK;
+}
+
+extern "C" int snk_comm_bench(snk_handle* h, int32_t iters, double* mean_us) {
+  if (!h || !mean_us || iters < 1) return fail(SNK_EINVAL, "bad argument");
+  if (!h->comm) return fail(SNK_EINVAL, "no communicator (snk_comm_init)");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+  double* scratch = h->d_global;  // in place on the result slots: the values are rewritten by the next step's reduction
+  for (int i = 0; i < 5; ++i) NCCL_TRY(g_nccl.AllReduce(h->d_snap, scratch, SNK_NSTATS, kNcclFloat64, kNcclSum, h->comm, h->side));
+  CUDA_TRY(cudaEventRecord(a, h->side));
+  for (int i = 0; i < iters; ++i) NCCL_TRY(g_nccl.AllReduce(h->d_snap, scratch, SNK_NSTATS, kNcclFloat64, kNcclSum, h->comm, h->side));
+  CUDA_TRY(cudaEventRecord(b, h->side));
+  CUDA_TRY(cudaStreamSynchronize(h->side));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *mean_us = (double)ms * 1e3 / iters;
+  return SNK_OK;
+}
+
+extern "C" int snk_comm_info(const snk_handle* h, int32_t* out /*[4]: ranks, rank, collectives issued (low 31 bits), nccl version*/) {
+  if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
+  out[0] = h->comm ? h->comm_ranks : 1; out[1] = h->comm_rank; out[2] = (int32_t)(h->collectives & 0x7fffffff);
+  int v = 0;
+  if (g_nccl.so && g_nccl.GetVersion) g_nccl.GetVersion(&v);
+  out[3] = v;
   return SNK_OK;
 }
 

@@ -61,6 +61,8 @@ struct Params {
   float* fin_ret;
   int32_t* fin_len;
   double* stats;
+  double* snap;                 // per-step copy of `stats` written by the last CTA of a step kernel (NULL: no per-step reduction)
+  u32* ticket;                  // arrival counter behind `snap`
   u32* err;
   const u32* tape_vals;
   const u32* tape_bounds;

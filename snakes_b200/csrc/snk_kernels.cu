@@ -76,6 +76,27 @@ __device__ __forceinline__ void flush_stats(const Params& p, const WarpStats& st
   }
 }
 
+// End of every step kernel: the CTA's sums go to the handle's running statistics.  When the handle reduces its
+// statistics over the ranks every step (snk_comm_init: Params::snap set), the LAST CTA to arrive also copies the vector
+// into the snapshot slot of this step, which the side stream hands to ncclAllReduce while the next step runs
+// (monitor.py:57-78 aggregated over all shards).
+__device__ __forceinline__ void publish_stats(const Params& p, const double* s_stats, int tid) {
+  __shared__ int s_last;
+  __syncthreads();
+  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+  if (p.snap) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (tid < SNK_NSTATS) p.snap[tid] = __ldcg(&p.stats[tid]);
+      if (tid == 0) *p.ticket = 0;
+    }
+  }
+}
+
 template <int RULES>
 __device__ __forceinline__ void advance_env(const Params& p, long long e, int lane, u32* sc, u32* bm, u32& errs, WarpStats& st) {
   u16* rings = p.body + e * p.S * p.cap;
@@ -182,8 +203,7 @@ __global__ void __launch_bounds__(BLOCK) k_step_tile(const Params p) {
   }
   if (tid == 0) bulk_wait_all();
   flush_stats(p, st, errs, s_stats, lane);
-  __syncthreads();
-  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+  publish_stats(p, s_stats, tid);
 }
 
 
@@ -281,8 +301,7 @@ __global__ void __launch_bounds__(128) k_lane_logic(const Params p) {
     if (valid) lane_store<S>(p, e, env);
   }
   reduce_lane_stats(p, st, errs, s_stats, lane);
-  __syncthreads();
-  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+  publish_stats(p, s_stats, tid);
 }
 
 // k_lane_paint: the observation writer.  Each warp owns one shared-memory image of TE envs holding
@@ -407,8 +426,7 @@ __global__ void __launch_bounds__(160, 5) k_step_lane_ws(const Params p) {
     }
   }
   reduce_lane_stats(p, st, errs, s_stats, lane);
-  __syncthreads();
-  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+  publish_stats(p, s_stats, tid);
 }
 
 
@@ -523,8 +541,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next launch may start its prologue
   if (lane == 0) bulk_wait_all();
   reduce_lane_stats(p, st, errs, s_stats, lane);
-  __syncthreads();
-  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+  publish_stats(p, s_stats, tid);
 }
 
 template <int RULES>
@@ -581,8 +598,7 @@ __global__ void __launch_bounds__(256) k_step_dense(const Params p) {
     __syncthreads();
   }
   if (warp == 0) flush_stats(p, st, errs, s_stats, lane);
-  __syncthreads();
-  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+  publish_stats(p, s_stats, tid);
 }
 
 
@@ -791,8 +807,7 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
   st.len_sum = st.fruits = st.deaths = st.cells = st.draws = 0.f;
 #endif
   if (warp == 0) flush_stats(p, st, errs, s_stats, lane);
-  __syncthreads();
-  if (tid < SNK_NSTATS && s_stats[tid] != 0.0) atomicAdd(&p.stats[tid], s_stats[tid]);
+  publish_stats(p, s_stats, tid);
 }
 
 // The file can be compiled as one translation unit (SNK_TU undefined) or as four that build in
@@ -966,19 +981,21 @@ __global__ void k_gae(const float* __restrict__ rewards, const float* __restrict
 
 // ------------------------------------------------------------------ state dump / load, action stream
 // canonical blob <-> private layout; one thread per (env, snake); not on the hot path
-__global__ void k_dump(const Params p, u8* blob, snk_state_layout lay) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+__global__ void k_dump(const Params p, u8* blob, snk_state_layout lay, long long first, long long count) {
+  // `lay` is the layout of a blob of `count` envs; local env el of the blob is env first + el of the handle
+  const long long il = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int S = p.S, cap = p.cap;
-  if (i >= p.N * S) return;
-  const long long e = i / S;
-  const int s = (int)(i - e * S);
+  if (il >= count * S) return;
+  const long long el = il / S, e = first + el;
+  const int s = (int)(il - el * S);
+  const long long i = e * S + s;
   const u32* r = p.rec + e * p.RW;
   const u32 a = r[REC_SNAKE0 + 2 * s], b = r[REC_SNAKE0 + 2 * s + 1];
   const int len = a >> 16, hs = a & 0xffff;
-  reinterpret_cast<u16*>(blob + lay.off_len)[i] = (u16)len;
-  reinterpret_cast<u16*>(blob + lay.off_grow_to)[i] = (u16)(b & 0xffff);
-  (blob + lay.off_vel)[i] = (u8)(b >> 16);
-  u16* dst = reinterpret_cast<u16*>(blob + lay.off_body) + i * cap;
+  reinterpret_cast<u16*>(blob + lay.off_len)[il] = (u16)len;
+  reinterpret_cast<u16*>(blob + lay.off_grow_to)[il] = (u16)(b & 0xffff);
+  (blob + lay.off_vel)[il] = (u8)(b >> 16);
+  u16* dst = reinterpret_cast<u16*>(blob + lay.off_body) + il * cap;
   if (p.family == 1) {  // chain code: hs is the head id
     const u32* ch = p.chain + i * p.CW;
     const u32 c0 = r[s < 3 ? 5 + s : p.RW - 2];  // LaneRec::c0_word
@@ -989,23 +1006,25 @@ __global__ void k_dump(const Params p, u8* blob, snk_state_layout lay) {
     for (int k = 0; k < cap; ++k) dst[k] = k < len ? (u16)ring_at(ring, hs, k, cap) : (u16)0;
   }
   if (s == 0) {
-    reinterpret_cast<int32_t*>(blob + lay.off_t)[e] = (int32_t)r[REC_T];
-    reinterpret_cast<u32*>(blob + lay.off_spare)[e] = r[REC_SPARE];
-    reinterpret_cast<u32*>(blob + lay.off_draw_ctr)[e] = r[REC_DRAW_CTR];
-    reinterpret_cast<u32*>(blob + lay.off_ep_ret)[e] = r[REC_EP_RET];
-    reinterpret_cast<int32_t*>(blob + lay.off_ep_len)[e] = (int32_t)r[REC_EP_LEN];
+    reinterpret_cast<int32_t*>(blob + lay.off_t)[el] = (int32_t)r[REC_T];
+    reinterpret_cast<u32*>(blob + lay.off_spare)[el] = r[REC_SPARE];
+    reinterpret_cast<u32*>(blob + lay.off_draw_ctr)[el] = r[REC_DRAW_CTR];
+    reinterpret_cast<u32*>(blob + lay.off_ep_ret)[el] = r[REC_EP_RET];
+    reinterpret_cast<int32_t*>(blob + lay.off_ep_len)[el] = (int32_t)r[REC_EP_LEN];
     if (lay.fruit_is_grid && p.family == 1) {
       for (int k = 0; k < p.VV; ++k)
-        (blob + lay.off_fruit)[e * p.VV + k] = ((p.gbits[e * p.GBW + (k >> 5)] >> (k & 31)) & 1) ? p.grid[e * p.grid_stride + k] : (u8)0;
+        (blob + lay.off_fruit)[el * p.VV + k] = ((p.gbits[e * p.GBW + (k >> 5)] >> (k & 31)) & 1) ? p.grid[e * p.grid_stride + k] : (u8)0;
     } else if (lay.fruit_is_grid) {
-      for (int k = 0; k < p.VV; ++k) (blob + lay.off_fruit)[e * p.VV + k] = p.grid[e * p.grid_stride + k];
+      for (int k = 0; k < p.VV; ++k) (blob + lay.off_fruit)[el * p.VV + k] = p.grid[e * p.grid_stride + k];
     } else {
       const u16* fr = reinterpret_cast<const u16*>(r + REC_SNAKE0 + 2 * S);
-      for (int k = 0; k < p.F; ++k) reinterpret_cast<u16*>(blob + lay.off_fruit)[e * p.F + k] = fr[k];
+      for (int k = 0; k < p.F; ++k) reinterpret_cast<u16*>(blob + lay.off_fruit)[el * p.F + k] = fr[k];
     }
   }
 }
 
+// snk_load_state trusts nothing: a body longer than the board, a cell id outside the padded grid, a velocity code above 4
+// or two consecutive segments that are not adjacent cells raise SNK_DEVERR_BAD_STATE and leave that snake empty.
 __global__ void k_load(const Params p, const u8* blob, snk_state_layout lay) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int S = p.S, cap = p.cap;
@@ -1013,26 +1032,34 @@ __global__ void k_load(const Params p, const u8* blob, snk_state_layout lay) {
   const long long e = i / S;
   const int s = (int)(i - e * S);
   u32* r = p.rec + e * p.RW;
-  const u32 len = reinterpret_cast<const u16*>(blob + lay.off_len)[i];
+  u32 len = reinterpret_cast<const u16*>(blob + lay.off_len)[i];
   const u32 grow = reinterpret_cast<const u16*>(blob + lay.off_grow_to)[i];
-  const u32 vel = (blob + lay.off_vel)[i];
-  r[REC_SNAKE0 + 2 * s + 1] = grow | (vel << 16);
+  u32 vel = (blob + lay.off_vel)[i];
   const u16* src = reinterpret_cast<const u16*>(blob + lay.off_body) + i * cap;
+  bool bad = len > (u32)(p.D * p.D + 1) || len > (u32)cap || vel > 4u;
+  for (u32 k = 0; k < len && !bad; ++k) bad = src[k] >= (u32)p.VV;
+  if (p.family == 1) {
+    for (u32 k = 0; k + 1 < len && !bad; ++k) {
+      const int diff = (int)src[k] - (int)src[k + 1];
+      bad = !(diff == p.V || diff == 1 || diff == -p.V || diff == -1);
+    }
+  }
+  if (bad) { atomicOr(p.err, SNK_DEVERR_BAD_STATE); len = 0; vel = 0; }
+  r[REC_SNAKE0 + 2 * s + 1] = grow | (vel << 16);
   if (p.family == 1) {  // chain code: direction of segment k+1 -> k, 16 per word
-    r[REC_SNAKE0 + 2 * s] = (u32)src[0] | (len << 16);
+    r[REC_SNAKE0 + 2 * s] = (len ? (u32)src[0] : 0u) | (len << 16);
     u32* ch = p.chain + i * p.CW;
     for (int k = 0; k < p.CW; ++k) ch[k] = 0;
     for (int k = 0; k + 1 < (int)len; ++k) {
       const int diff = (int)src[k] - (int)src[k + 1];
-      const u32 d = diff == p.V ? 0u : diff == 1 ? 1u : diff == -p.V ? 2u : diff == -1 ? 3u : 4u;
-      if (d == 4u) { atomicOr(p.err, SNK_DEVERR_BAD_STATE); break; }
+      const u32 d = diff == p.V ? 0u : diff == 1 ? 1u : diff == -p.V ? 2u : 3u;
       ch[k >> 4] |= d << (2 * (k & 15));
     }
     r[s < 3 ? 5 + s : p.RW - 2] = ch[0];  // LaneRec::c0_word
   } else {
     r[REC_SNAKE0 + 2 * s] = 0u | (len << 16);
     u16* ring = p.body + i * cap;
-    for (int k = 0; k < cap; ++k) ring[k] = src[k];
+    for (int k = 0; k < cap; ++k) ring[k] = k < (int)len ? src[k] : (u16)0;
   }
   if (s == 0) {
     r[REC_T] = (u32) reinterpret_cast<const int32_t*>(blob + lay.off_t)[e];
@@ -1052,8 +1079,32 @@ __global__ void k_load(const Params p, const u8* blob, snk_state_layout lay) {
       }
     } else {
       u16* fr = reinterpret_cast<u16*>(r + REC_SNAKE0 + 2 * S);
-      for (int k = 0; k < p.F; ++k) fr[k] = reinterpret_cast<const u16*>(blob + lay.off_fruit)[e * p.F + k];
+      for (int k = 0; k < p.F; ++k) {
+        const u16 f = reinterpret_cast<const u16*>(blob + lay.off_fruit)[e * p.F + k];
+        if (f >= (u32)p.VV) { atomicOr(p.err, SNK_DEVERR_BAD_STATE); fr[k] = (u16)(p.V + 1); } else fr[k] = f;
+      }
     }
+  }
+}
+
+// The first n_out views of every pixel, packed: [pixels][3K] -> [pixels][3 n_out].  Used by the host-buffer step when
+// the caller only keeps the main snake's view (ppo_multi_agent_new.py:181 stores obs[..., 0:3] alone): the D2H copy then
+// carries n_out / K of the bytes.  One thread per 4 pixels (12 n_out bytes = 3 n_out aligned words).
+__global__ void k_extract_views(const u8* __restrict__ src, u8* __restrict__ dst, long long n_pixels, int C, int n_out) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long px0 = g * 4;
+  if (px0 >= n_pixels) return;
+  const int CO = 3 * n_out;
+  if (px0 + 4 <= n_pixels) {
+    u32 w[12];  // n_out <= 4
+    u8* b = reinterpret_cast<u8*>(w);
+    for (int q = 0; q < 4; ++q)
+      for (int j = 0; j < CO; ++j) b[q * CO + j] = src[(px0 + q) * C + j];
+    u32* d = reinterpret_cast<u32*>(dst + px0 * CO);
+    for (int j = 0; j < CO; ++j) d[j] = w[j];
+  } else {
+    for (long long q = px0; q < n_pixels; ++q)
+      for (int j = 0; j < CO; ++j) dst[q * CO + j] = src[q * C + j];
   }
 }
 
@@ -1212,9 +1263,15 @@ cudaError_t snk_launch_upscale84(const uint8_t* native, uint8_t* out, long long 
   return launch_upscale<0, 0>(native, out, N, V, C, n_sm, stream);
 }
 
-cudaError_t snk_launch_dump(const Params& p, u8* blob, const snk_state_layout& lay, cudaStream_t stream) {
-  const long long n = p.N * p.S;
-  k_dump<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, blob, lay);
+cudaError_t snk_launch_dump(const Params& p, u8* blob, const snk_state_layout& lay, long long first, long long count, cudaStream_t stream) {
+  const long long n = count * p.S;
+  k_dump<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, blob, lay, first, count);
+  return cudaGetLastError();
+}
+
+cudaError_t snk_launch_extract_views(const uint8_t* src, uint8_t* dst, long long n_pixels, int C, int n_out, cudaStream_t stream) {
+  const long long n = (n_pixels + 3) / 4;
+  k_extract_views<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n_pixels, C, n_out);
   return cudaGetLastError();
 }
 

@@ -6,10 +6,13 @@ a `SubprocVecEnv` (src/baselines/common/vec_env/subproc_vec_env.py:31) of
 `observation_space`, `action_space`, `reset()`, `step_async()`, `step_wait()`, `step()`,
 `close()` (src/baselines/common/vec_env/__init__.py:22-88) -- but all N envs live in HBM and
 one fused kernel steps them.  Observations, rewards and dones are returned as CUDA tensors that
-alias the library's buffers (no copy, no host round trip); `host_io=True` returns numpy arrays
-exactly like SubprocVecEnv.step_wait (`:57-61`).
+alias the library's buffers (no copy, no host round trip: consume them before the next step, or
+clone); `host_io=True` returns numpy arrays like SubprocVecEnv.step_wait (`:57-61`): float64
+rewards, bool dones, fresh arrays every step (`host_copy=False` hands out views of the pinned
+staging buffers instead, for callers that consume an observation before the next step).
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -44,17 +47,36 @@ def tile_images(img_nhwc):
 class Infos(object):
     """Lazily materialised `infos` of one step: behaves like the tuple of per-env dicts that
     SubprocVecEnv returns ({'ale.lives': 1, 'num_snakes': n[, 'episode': {'r','l','t'}]},
-    snake_multiple_test.py:197 + monitor.py:62-76) but only touches the host when indexed."""
+    snake_multiple_test.py:197 + monitor.py:62-76) but only touches the host when indexed.
 
-    def __init__(self, num_alive, done, ep_ret, ep_len, elapsed):
+    Like SubprocVecEnv's infos it describes ITS step for good: the env snapshots the (small)
+    device arrays behind an Infos object that is still alive and unread when the next step is
+    launched (`_freeze`), so reading it later never reports the next step's episodes."""
+
+    def __init__(self, num_alive, done, ep_ret, ep_len, elapsed, block=None):
         self._dev = (num_alive, done, ep_ret, ep_len)
+        self._block = block      # the one device block the four arrays live in (snk_buffers.d_info_block)
         self._host = None
         self._elapsed = elapsed
         self._n = int(done.shape[0])
 
+    def _freeze(self):
+        """Called by the env before it overwrites the live buffers: keep this step's values."""
+        if self._host is not None or not isinstance(self._dev[0], torch.Tensor):
+            return
+        if self._block is not None:
+            snap = self._block.clone()   # one copy: the four arrays share a block
+            base = self._block.data_ptr()
+            self._dev = tuple(snap[x.data_ptr() - base: x.data_ptr() - base + x.numel() * x.element_size()].view(x.dtype)
+                              for x in self._dev)
+        else:
+            self._dev = tuple(x.clone() for x in self._dev)
+        self._block = None
+
     def _fetch(self):
         if self._host is None:
             self._host = tuple(np.asarray(x.cpu() if isinstance(x, torch.Tensor) else x) for x in self._dev)
+            self._dev = self._block = None
         return self._host
 
     def __len__(self):
@@ -82,6 +104,30 @@ class Infos(object):
         return [{"r": round(float(ret[i]), 6), "l": int(length[i]), "t": self._elapsed} for i in idx]
 
 
+class StepGraph(object):
+    """T env steps captured as one CUDA graph (snk_graph_create): a single launch per rollout,
+    kernels linked by programmatic dependent-launch edges, no Python in the loop."""
+
+    def __init__(self, env, handle, keep):
+        self._env, self._g, self._keep = env, handle, keep
+
+    def launch(self):
+        self._env._before_overwrite()
+        _lib.check(self._env._L.snk_graph_launch(self._g, self._env._stream()))
+
+    def close(self):
+        if self._g is not None and not self._env.closed:
+            torch.cuda.synchronize(self._env.device)
+            self._env._L.snk_graph_destroy(self._g)
+        self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SnakeVecEnv(object):
     """N multi-snake envs stepped in lockstep on one GPU.
 
@@ -92,12 +138,18 @@ class SnakeVecEnv(object):
     `env_id_base` (global id of env 0: shard offset under multi-GPU), `auto_reset`, `obs_mode`
     ('native' [V,V,3K] or 'atari84' [84,84,3K]: the reference's WarpFrame, utils.py:15-31; exact
     pixel replication, so it needs 84 % (size + 2) == 0, e.g. size 10 or 19).
+    Host I/O: `host_io=True` (numpy in / numpy out), `host_views` (how many views of each pixel
+    come back, default all K; 1 = the main snake's view only, ppo_multi_agent_new.py:181),
+    `host_copy` (default True: fresh arrays every step like np.stack; False: views of the pinned,
+    NUMA-local staging buffers).  `debug`: experiment switches, a "key=value,..." string
+    (include/snk.h, snk_create_ex); None reads the SNK_DEBUG environment variable.
     """
 
     def __init__(self, num_envs, size=(10, 10), n_snakes=2, n_fruits=None, n_views=None, rules="classic",
                  seed=0, device=0, env_id_base=0, auto_reset=True, max_steps=2000, screen_res=300, host_io=False,
-                 obs_mode="native"):
+                 obs_mode="native", host_views=None, host_copy=True, debug=None):
         import time
+        self.closed = True
         self._L = _lib.lib()
         if isinstance(device, torch.device):
             device = device.index or 0
@@ -112,8 +164,13 @@ class SnakeVecEnv(object):
         self.device = torch.device("cuda", self.cfg.device)
         torch.cuda.init()
         h = C.c_void_p()
-        _lib.check(self._L.snk_create(C.byref(self.cfg), C.byref(h)))
+        self._debug = debug
+        if debug is None:
+            _lib.check(self._L.snk_create(C.byref(self.cfg), C.byref(h)))
+        else:
+            _lib.check(self._L.snk_create_ex(C.byref(self.cfg), str(debug).encode(), C.byref(h)))
         self._h = h
+        self.closed = False
         self.lay = _lib.SnkStateLayout()
         _lib.check(self._L.snk_state_layout_of(C.byref(self.cfg), C.byref(self.lay)))
         self.num_envs = self.N = self.cfg.num_envs
@@ -122,6 +179,12 @@ class SnakeVecEnv(object):
         self.rules = rules
         self.screen_res = screen_res
         self.host_io = host_io
+        self.host_copy = bool(host_copy)
+        self.host_views = self.K if not host_views else int(host_views)
+        if not 1 <= self.host_views <= self.K:
+            raise ValueError("host_views must be 1..n_views")
+        self._last_infos = None
+        self._graphs = {}
         self.action_space = Discrete(6 if self.cfg.rules == _lib.RULES["cut"] else 5)
         self._bind_buffers()
         self.observation_space = Box(0, 255, tuple(self.obs.shape[1:]), np.uint8)
@@ -129,13 +192,24 @@ class SnakeVecEnv(object):
         self._pending = False
         self._tstart = time.time()
         self._time = time
-        self.closed = False
+        self.host_numa_node = None
         if host_io:
-            self._h_actions = torch.zeros((self.N, self.S), dtype=torch.int8).pin_memory()
-            self._h_obs = torch.zeros(tuple(self.obs.shape), dtype=torch.uint8).pin_memory()
-            self._h_reward = torch.zeros(self.N, dtype=torch.float32).pin_memory()
-            self._h_done = torch.zeros(self.N, dtype=torch.uint8).pin_memory()
-            self._h_alive = torch.zeros(self.N, dtype=torch.uint8).pin_memory()
+            # pinned staging buffers from the C layer, placed on the GPU's NUMA node (snk_host_alloc)
+            oshape = tuple(self.obs.shape[:3]) + (3 * self.host_views,)
+            self._h_actions = self._host_array((self.N, self.S), np.int8)
+            self._h_obs = self._host_array(oshape, np.uint8)
+            self._h_reward = self._host_array((self.N,), np.float32)
+            self._h_done = self._host_array((self.N,), np.uint8)
+            self._h_alive = self._host_array((self.N,), np.uint8)
+            self.observation_space = Box(0, 255, oshape[1:], np.uint8)
+
+    def _host_array(self, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr, node = C.c_void_p(), C.c_int32(-1)
+        _lib.check(self._L.snk_host_alloc(self._h, max(n, 1), C.byref(ptr), C.byref(node)))
+        self.host_numa_node = node.value
+        buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def _bind_buffers(self):
         b = _lib.SnkBuffers()
@@ -149,6 +223,8 @@ class SnakeVecEnv(object):
         self.episode_return = _alias(b.d_episode_return, (N,), "<f4", dev)
         self.episode_len = _alias(b.d_episode_len, (N,), "<i4", dev)
         self._stats = _alias(b.d_stats, (_lib.NSTATS,), "<f8", dev)
+        self._info_block = _alias(b.d_info_block, (b.info_block_bytes,), "|u1", dev)
+        self._own = (self.obs, self.rewards, self._done_u8)   # the handle's buffers (a rollout re-points the live names)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -165,26 +241,48 @@ class SnakeVecEnv(object):
             raise _lib.SnkError("seed() must be called before the first reset()")
         self.close()
         self.__init__(self.N, self.D, self.S, self.F, self.K, self.rules, seed, self.cfg.device, self.cfg.env_id_base,
-                      bool(self.cfg.auto_reset), self.cfg.max_steps, self.screen_res, self.host_io, self.obs_mode)
+                      bool(self.cfg.auto_reset), self.cfg.max_steps, self.screen_res, self.host_io, self.obs_mode,
+                      self.host_views, self.host_copy, self._debug)
         return [int(seed)]
+
+    def _before_overwrite(self):
+        """The live buffers are about to change: freeze the previous step's infos if somebody still holds them."""
+        li = self._last_infos() if self._last_infos is not None else None
+        if li is not None:
+            li._freeze()
+        self._last_infos = None
+        self.obs, self.rewards, self._done_u8 = self._own
+
+    def _host_obs(self):
+        """[N,H,W,3K] (or the first host_views views) of the current device observations as numpy."""
+        if self.host_views == self.K:
+            return self.obs.cpu().numpy()
+        return self.obs[..., :3 * self.host_views].contiguous().cpu().numpy()
 
     def reset(self, mask=None):
         """VecEnv.reset (subproc_vec_env.py:63-66).  `mask` (bool [N], optional extension) resets a subset."""
         m = None
         if mask is not None:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        self._before_overwrite()
         _lib.check(self._L.snk_reset(self._h, C.c_void_p(m.data_ptr()) if m is not None else None, self._stream()))
         if self.host_io:
-            return self.obs.cpu().numpy()
+            return self._host_obs()
         return self.obs
 
     def step_async(self, actions):
         """actions: [N][S] ints -- a CUDA int8 tensor is used as is; sequences of tuples (what
-        MultiModel.multi_step builds, ppo_multi_agent_new.py:35-37) and numpy arrays are copied."""
+        MultiModel.multi_step builds, ppo_multi_agent_new.py:35-37) and numpy arrays are copied.
+        The step (with host_io: the H2D copy, the step and the D2H copies) is enqueued here;
+        step_wait hands out the results."""
         if self._pending:
             raise _lib.SnkError("already running an async step")
+        self._before_overwrite()
         if self.host_io:
-            self._h_actions.copy_(torch.as_tensor(np.asarray(actions).reshape(self.N, self.S)).to(torch.int8))
+            self._h_actions[...] = np.asarray(actions).reshape(self.N, self.S)
+            p = lambda a: C.c_void_p(a.ctypes.data)
+            _lib.check(self._L.snk_step_host_async(self._h, p(self._h_actions), p(self._h_obs), self.host_views, p(self._h_reward),
+                                                   p(self._h_done), p(self._h_alive), self._stream()))
         else:
             if isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.int8 and actions.is_contiguous():
                 a = actions.view(self.N, self.S)
@@ -202,23 +300,27 @@ class SnakeVecEnv(object):
         self._pending = False
         elapsed = round(self._time.time() - self._tstart, 6)
         if self.host_io:
-            _lib.check(self._L.snk_step_host(
-                self._h, C.c_void_p(self._h_actions.data_ptr()), C.c_void_p(self._h_obs.data_ptr()),
-                C.c_void_p(self._h_reward.data_ptr()), C.c_void_p(self._h_done.data_ptr()),
-                C.c_void_p(self._h_alive.data_ptr()), self._stream()))
-            done = self._h_done.numpy().astype(bool)
-            infos = Infos(self._h_alive.numpy(), done, self.episode_return, self.episode_len, elapsed)
-            return self._h_obs.numpy(), self._h_reward.numpy(), done, infos
+            # Monitor's r / l of the envs that finished, fetched behind the big copies (two [N] arrays)
+            ret, length = self.episode_return.cpu().numpy(), self.episode_len.cpu().numpy()  # synchronises the stream
+            done = self._h_done.astype(bool)
+            infos = Infos(self._h_alive.copy(), done, ret, length, elapsed)
+            obs = self._h_obs.copy() if self.host_copy else self._h_obs
+            return obs, self._h_reward.astype(np.float64), done, infos  # np.stack of python floats is float64 (:61)
         dones = self._done_u8.view(torch.bool)
-        return self.obs, self.rewards, dones, Infos(self.num_alive, self._done_u8, self.episode_return, self.episode_len, elapsed)
+        infos = Infos(self.num_alive, self._done_u8, self.episode_return, self.episode_len, elapsed, self._info_block)
+        self._last_infos = weakref.ref(infos)
+        return self.obs, self.rewards, dones, infos
 
     def step(self, actions):
         self.step_async(actions)
         return self.step_wait()
 
     def close(self):
-        if not self.closed and getattr(self, "_h", None):
+        if not getattr(self, "closed", True) and getattr(self, "_h", None):
             torch.cuda.synchronize(self.device)
+            for g in list(self._graphs.values()):
+                g.close()
+            self._graphs = {}
             self._L.snk_destroy(self._h)
             self._h = None
         self.closed = True
@@ -275,14 +377,36 @@ class SnakeVecEnv(object):
             _lib.check(self._L.snk_set_obs_target(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel()))
         self._bind_buffers()
 
+    def make_graph(self, actions, T=None, obs_out=None, rewards_out=None, dones_out=None, sync_back=False):
+        """T steps as one CUDA graph launch (snk_graph_create).  actions: int8 CUDA tensor [B, N, S]; step t plays
+        batch t % B (T defaults to B).  obs_out [T,N,H,W,3K] / rewards_out [T,N] f32 / dones_out [T,N] u8 redirect the
+        per-step outputs into rollout slots; without them every step writes the env's own buffers."""
+        a = actions
+        assert a.is_cuda and a.dtype == torch.int8 and a.is_contiguous() and tuple(a.shape[1:]) == (self.N, self.S)
+        B = int(a.shape[0])
+        T = B if T is None else int(T)
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        g = C.c_void_p()
+        _lib.check(self._L.snk_graph_create(self._h, ptr(a), B, T, ptr(obs_out), ptr(rewards_out), ptr(dones_out),
+                                            _lib.GRAPH_SYNC_BACK if sync_back else 0, C.byref(g)))
+        return StepGraph(self, g, (a, obs_out, rewards_out, dones_out))
+
+    def make_scripted_graph(self, T, step0=0, seed=1, eps=0.05):
+        """T steps of [fruit-seeking policy kernel, step kernel] as one CUDA graph launch (snk_graph_create_scripted)."""
+        g = C.c_void_p()
+        _lib.check(self._L.snk_graph_create_scripted(self._h, int(T), int(step0), int(seed), int(round(eps * 1000)), C.byref(g)))
+        return StepGraph(self, g, None)
+
     def rollout(self, actions, obs_out=None, rewards_out=None, dones_out=None):
         """T steps back to back into rollout buffers on the device (the mb_obs / mb_rewards /
-        mb_dones of Runner.run, ppo_multi_agent_new.py:178-198) with no host round trip.
-        actions: int8 CUDA tensor [T, N, S].  Returns (obs [T,N,H,W,3K] u8, rewards [T,N] f32, dones [T,N] bool)."""
+        mb_dones of Runner.run, ppo_multi_agent_new.py:178-198) with no host round trip: ONE graph
+        launch (cached per buffer set).  actions: int8 CUDA tensor [T, N, S].  Returns (obs
+        [T,N,H,W,3K] u8, rewards [T,N] f32, dones [T,N] bool); afterwards `env.obs` / `env.rewards`
+        are the last slot of those buffers (no copy back) until the next step() or reset()."""
         a = torch.as_tensor(actions, device=self.device).to(torch.int8).contiguous()
         T = int(a.shape[0])
         assert tuple(a.shape) == (T, self.N, self.S)
-        shape = (T,) + tuple(self.obs.shape)
+        shape = (T,) + tuple(self._own[0].shape)
         if obs_out is None:
             obs_out = torch.empty(shape, dtype=torch.uint8, device=self.device)
         if rewards_out is None:
@@ -290,10 +414,17 @@ class SnakeVecEnv(object):
         if dones_out is None:
             dones_out = torch.empty((T, self.N), dtype=torch.uint8, device=self.device)
         assert obs_out.is_contiguous() and tuple(obs_out.shape) == shape and obs_out.dtype == torch.uint8
-        _lib.check(self._L.snk_rollout(self._h, C.c_void_p(a.data_ptr()), T, C.c_void_p(obs_out.data_ptr()),
-                                       C.c_void_p(rewards_out.data_ptr()), C.c_void_p(dones_out.data_ptr()), self._stream()))
-        self._a_live = a
-        return obs_out, rewards_out, dones_out.view(torch.bool) if dones_out.dtype == torch.uint8 else dones_out
+        d8 = dones_out.view(torch.uint8) if dones_out.dtype == torch.bool else dones_out
+        key = (a.data_ptr(), T, obs_out.data_ptr(), rewards_out.data_ptr(), d8.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            for old in self._graphs.values():   # one cached rollout graph at a time
+                old.close()
+            self._graphs = {}
+            g = self._graphs[key] = self.make_graph(a, T, obs_out, rewards_out, d8)
+        g.launch()
+        self.obs, self.rewards, self._done_u8 = obs_out[T - 1], rewards_out[T - 1], d8[T - 1]
+        return obs_out, rewards_out, d8.view(torch.bool)
 
     def set_draw_tape(self, vals, bounds, offsets):
         """Replay mode: recorded reference draws, CSR per env (parity tests)."""
@@ -304,6 +435,7 @@ class SnakeVecEnv(object):
         _lib.check(self._L.snk_set_draw_tape(self._h, vals.ctypes.data_as(C.c_void_p),
                                              None if b is None else b.ctypes.data_as(C.c_void_p),
                                              offsets.ctypes.data_as(C.c_void_p)))
+        self.cfg.rng_mode = _lib.RNG_TAPE
 
     def dump_state_blob(self):
         blob = np.zeros(self.lay.total_bytes, dtype=np.uint8)
@@ -316,6 +448,16 @@ class SnakeVecEnv(object):
 
     def dump_state(self):
         return split_state(self.dump_state_blob(), self.lay, self.cfg)
+
+    def dump_state_range(self, first, count):
+        """Canonical state of envs [first, first + count) only (snk_dump_state_range)."""
+        sub = _lib.SnkConfig.from_buffer_copy(self.cfg)
+        sub.num_envs, sub.env_id_base = int(count), self.cfg.env_id_base + int(first)
+        lay = _lib.SnkStateLayout()
+        _lib.check(self._L.snk_state_layout_of(C.byref(sub), C.byref(lay)))
+        blob = np.zeros(lay.total_bytes, dtype=np.uint8)
+        _lib.check(self._L.snk_dump_state_range(self._h, int(first), int(count), blob.ctypes.data_as(C.c_void_p), blob.nbytes))
+        return split_state(blob, lay, sub)
 
     def save(self, path):
         """Checkpoint of the env state (the reference never checkpoints it; its learner only saves
@@ -353,13 +495,50 @@ class SnakeVecEnv(object):
 
     def stats(self, reduce=True):
         """Running episode statistics (Monitor's aggregate role).  With torch.distributed
-        initialised and reduce=True the 8 doubles are summed over all ranks (NCCL all-reduce):
-        the only inter-GPU traffic of the env."""
+        initialised and reduce=True the 8 doubles are summed over all ranks on demand (a
+        torch.distributed all-reduce); the in-loop form is init_comm() + stats_global()."""
         from .sharding import all_reduce_stats
         s = self._stats.clone()
         if reduce:
             all_reduce_stats(s)
         return dict(zip(_lib.STAT_NAMES, s.cpu().tolist()))
+
+    def init_comm(self, group=None):
+        """Sets up the path's one collective (snk_comm_init): from now on every step all-reduces the
+        8-double statistics vector over all ranks on a side stream (raw ncclAllReduce issued by the
+        C layer), read one step late through stats_global().  The NCCL id travels over the existing
+        torch.distributed group; without one (single process) this is a one-rank communicator."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _lib.check(self._L.snk_comm_unique_id(ident.ctypes.data_as(C.c_void_p)))
+        if world > 1:
+            on_gpu = dist.get_backend(group) == "nccl"
+            t = torch.from_numpy(ident).to(self.device if on_gpu else "cpu")
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            ident = np.ascontiguousarray(t.cpu().numpy())
+        torch.cuda.synchronize(self.device)
+        _lib.check(self._L.snk_comm_init(self._h, ident.ctypes.data_as(C.c_void_p), world, rank))
+        return world
+
+    def stats_global(self):
+        """Statistics summed over all ranks as of the last completed per-step reduction (after init_comm)."""
+        out = np.zeros(_lib.NSTATS, dtype=np.float64)
+        _lib.check(self._L.snk_get_stats_global(self._h, out.ctypes.data_as(C.c_void_p), self._stream()))
+        return dict(zip(_lib.STAT_NAMES, out.tolist()))
+
+    def comm_latency_us(self, iters=200):
+        """Mean duration of one all-reduce of the statistics vector (CUDA events on the side stream; collective call)."""
+        out = C.c_double(0)
+        _lib.check(self._L.snk_comm_bench(self._h, int(iters), C.byref(out)))
+        return out.value
+
+    def comm_info(self):
+        out = (C.c_int32 * 4)()
+        _lib.check(self._L.snk_comm_info(self._h, out))
+        return dict(zip(("ranks", "rank", "allreduces", "nccl_version"), list(out)))
 
     def reset_stats(self):
         _lib.check(self._L.snk_reset_stats(self._h, self._stream()))

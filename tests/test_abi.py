@@ -69,6 +69,19 @@ def test_bad_arguments_are_reported_not_crashed(L):
     out = C.c_void_p()
     too_many = L.make_config(4, 10, 64)
     assert lib.snk_create(C.byref(too_many), C.byref(out)) == -1 and not out.value
+    # header and cfg_check agree: n_fruits 0..32, env_id_base >= 0, global ids within 32 bits
+    assert lib.snk_state_layout_of(C.byref(L.make_config(4, 10, 2, 32)), C.byref(lay)) == 0
+    assert lib.snk_state_layout_of(C.byref(L.make_config(4, 10, 2, 33)), C.byref(lay)) == -1
+    assert lib.snk_state_layout_of(C.byref(L.make_config(4, 10, 2, env_id_base=-2)), C.byref(lay)) == -1
+    assert b"env_id_base" in lib.snk_last_error()
+    assert lib.snk_state_layout_of(C.byref(L.make_config(4, 10, 2, env_id_base=(1 << 32) - 3)), C.byref(lay)) == -1
+    assert "0..32" in open(os.path.join(ROOT, "include", "snk.h")).read()
+    # the entry points added in round 2 validate their arguments too
+    assert lib.snk_graph_create(None, None, 1, 1, None, None, None, 0, None) == -1
+    assert lib.snk_graph_launch(None, None) == -1 and lib.snk_graph_destroy(None) == 0
+    assert lib.snk_comm_init(None, None, 1, 0) == -1 and lib.snk_comm_unique_id(None) == -1
+    assert lib.snk_host_alloc(None, 16, None, None) == -1 and lib.snk_dump_state_range(None, 0, 1, None, 0) == -1
+    assert set(L.DEVERR) == {1, 2, 4, 8, 16}
 
 
 def test_product_does_not_import_oracle():

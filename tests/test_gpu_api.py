@@ -74,10 +74,147 @@ def test_host_io_matches_device_path(sb):
         a = dev.gen_actions(t, 7).cpu().numpy()
         od, rd, dd, _ = dev.step(a)
         oh, rh, dh, ih = host.step(a)
-        assert isinstance(oh, np.ndarray) and oh.dtype == np.uint8 and rh.dtype == np.float32 and dh.dtype == bool
+        assert isinstance(oh, np.ndarray) and oh.dtype == np.uint8 and rh.dtype == np.float64 and dh.dtype == bool
         assert np.array_equal(od.cpu().numpy(), oh) and np.array_equal(rd.cpu().numpy(), rh) and np.array_equal(dd.cpu().numpy(), dh)
         assert ih[0]["num_snakes"] == int(dev.num_alive[0])
     dev.close(); host.close()
+
+
+def test_host_io_returns_fresh_arrays(sb):
+    """SubprocVecEnv.step_wait returns new np.stack arrays every step and the reference Runner appends them without a
+    copy (ppo_multi_agent_new.py:196 `mb_rewards.append(rewards)`): results of earlier steps must not change when the
+    env steps again.  host_copy=False (views of the pinned staging buffers) is the documented opt-out for obs only."""
+    kw = dict(size=10, n_snakes=2, seed=9)
+    host = sb.SnakeVecEnv(256, host_io=True, **kw)
+    dev = sb.SnakeVecEnv(256, **kw)
+    host.reset(); dev.reset()
+    kept, want = [], []
+    for t in range(12):
+        a = dev.gen_actions(t, 7).cpu().numpy()
+        o, r, d, info = host.step(a)
+        od, rd, dd, _ = dev.step(a)
+        kept.append((o, r, d, info))
+        want.append((od.cpu().numpy(), rd.cpu().numpy().astype(np.float64), dd.cpu().numpy(), dev.num_alive.cpu().numpy()))
+    assert len({id(k[0]) for k in kept}) == 12 and any(not np.array_equal(kept[0][1], k[1]) for k in kept[1:])
+    for (o, r, d, info), (wo, wr, wd, wa) in zip(kept, want):
+        assert np.array_equal(o, wo) and np.array_equal(r, wr) and np.array_equal(d, wd)
+        assert [info[i]["num_snakes"] for i in range(0, 256, 37)] == [int(wa[i]) for i in range(0, 256, 37)]
+    view = sb.SnakeVecEnv(64, host_io=True, host_copy=False, **kw)
+    view.reset()
+    o1 = view.step(np.zeros((64, 2), dtype=np.int8))[0]
+    o2 = view.step(np.ones((64, 2), dtype=np.int8))[0]
+    assert o1 is o2 or np.shares_memory(o1, o2)
+    assert view.host_numa_node is not None
+    for e in (host, dev, view):
+        e.close()
+
+
+def test_host_io_main_view_only(sb):
+    """host_views=1: only the main snake's view crosses PCIe (ppo_multi_agent_new.py:181 keeps obs[..., 0:3] alone)."""
+    kw = dict(size=19, n_snakes=2, seed=4)
+    full = sb.SnakeVecEnv(300, **kw)
+    main = sb.SnakeVecEnv(300, host_io=True, host_views=1, **kw)
+    assert main.observation_space.shape == (21, 21, 3)
+    assert np.array_equal(full.reset().cpu().numpy()[..., 0:3], main.reset())
+    for t in range(30):
+        a = full.gen_actions(t, 3).cpu().numpy()
+        of, rf, df, _ = full.step(a)
+        om, rm, dm, _ = main.step(a)
+        assert om.shape == (300, 21, 21, 3) and np.array_equal(of.cpu().numpy()[..., 0:3], om), t
+        assert np.array_equal(rf.cpu().numpy().astype(np.float64), rm) and np.array_equal(df.cpu().numpy(), dm)
+    full.close(); main.close()
+
+
+def test_infos_describe_their_own_step(sb):
+    """An Infos object read AFTER the next step still reports its own step (SubprocVecEnv infos are immutable)."""
+    N = 512
+    env = sb.SnakeVecEnv(N, size=10, n_snakes=2, seed=3)
+    env.reset()
+    held = []
+    for t in range(25):
+        _, _, dones, infos = env.step(env.gen_actions(t, 2))
+        held.append((infos, dones.cpu().numpy().copy(), env.num_alive.cpu().numpy().copy(),
+                     env.episode_return.cpu().numpy().copy(), env.episode_len.cpu().numpy().copy()))
+    assert sum(int(h[1].sum()) for h in held) > 50
+    for infos, d, alive, ret, length in held:  # all read late
+        eps = infos.episodes()
+        assert len(eps) == int(d.sum())
+        for i in list(np.flatnonzero(d)[:5]) + [0, N - 1]:
+            info = infos[int(i)]
+            assert info["num_snakes"] == int(alive[i])
+            assert ("episode" in info) == bool(d[i])
+            if d[i]:
+                assert info["episode"]["l"] == int(length[i]) and info["episode"]["r"] == round(float(ret[i]), 6)
+    env.close()
+
+
+def test_load_state_rejects_bad_blobs(sb):
+    """snk_load_state validates the blob: too-long bodies, cell ids off the padded grid and broken
+    adjacency return SNK_ESTATE instead of writing out of bounds."""
+    env = sb.SnakeVecEnv(8, size=10, n_snakes=2, seed=1)
+    env.reset()
+    env.step(env.gen_actions(0, 1))
+    good = env.dump_state_blob()
+    for field, value in (("len", 5000), ("body", 60000), ("vel", 9)):
+        blob = good.copy()
+        st = sb.split_state(blob, env.lay, env.cfg)
+        if field == "body":
+            st["body"][3, 1, 0] = value
+        else:
+            st[field][3, 1] = value
+        with pytest.raises(sb.SnkError):
+            env.load_state_blob(blob)
+    blob = good.copy()
+    st = sb.split_state(blob, env.lay, env.cfg)
+    st["len"][2, 0] = 3
+    st["body"][2, 0, :3] = [14, 15, 40]   # 15 -> 40 is not a neighbour step
+    with pytest.raises(sb.SnkError):
+        env.load_state_blob(blob)
+    env.load_state_blob(good)              # a valid blob still loads, and the error flag was consumed
+    env.check_errors()
+    env.close()
+
+
+def test_dump_state_range_equals_slice(sb):
+    for rules, S, D, N in (("classic", 2, 19, 1000), ("cut", 3, 10, 700), ("adversarial", 5, 12, 90)):
+        env = sb.SnakeVecEnv(N, size=D, n_snakes=S, rules=rules, seed=6, env_id_base=100)
+        env.reset()
+        for t in range(20):
+            env.step(env.gen_actions(t, 4))
+        whole = env.dump_state()
+        for first, count in ((0, 1), (0, N), (N - 33, 33), (N // 3, 200 if N > 500 else 40)):
+            part = env.dump_state_range(first, count)
+            for k in whole:
+                assert np.array_equal(part[k], whole[k][first:first + count]), (rules, first, count, k)
+        with pytest.raises(sb.SnkError):
+            env.dump_state_range(N - 1, 2)
+        env.close()
+
+
+def test_single_rank_comm_and_graph(sb):
+    """snk_comm_init with one rank: the per-step all-reduce runs (side stream, one per step, also inside a CUDA graph)
+    and stats_global() equals the local sums once the stream has drained."""
+    import torch
+    N, T = 2048, 24
+    env = sb.SnakeVecEnv(N, size=10, n_snakes=2, seed=2)
+    ref = sb.SnakeVecEnv(N, size=10, n_snakes=2, seed=2)
+    env.reset(); ref.reset()
+    assert env.init_comm() == 1
+    acts = torch.stack([ref.gen_actions(t, 5).clone() for t in range(T)])
+    for t in range(5):
+        env.step(acts[t]); ref.step(acts[t])
+    assert env.comm_info()["allreduces"] == 5 and env.comm_info()["ranks"] == 1
+    assert env.stats_global() == ref.stats(reduce=False)
+    g = env.make_graph(acts[5:])
+    g.launch()
+    for t in range(5, T):
+        ref.step(acts[t])
+    assert torch.equal(env.obs, ref.obs)
+    assert env.comm_info()["allreduces"] == T
+    assert env.stats_global() == ref.stats(reduce=False)
+    env.step(acts[0]); ref.step(acts[0])
+    assert env.stats_global() == ref.stats(reduce=False) and torch.equal(env.obs, ref.obs)
+    g.close(); env.close(); ref.close()
 
 
 def test_obs_target_rollout_slot(sb):

@@ -193,12 +193,11 @@ def test_known_answers(sb):
         env.close()
 
 
-def test_rows_kernel_small_fields(sb, monkeypatch):
+def test_rows_kernel_small_fields(sb):
     """The row-chunked CTA-per-env kernel forced onto boards whose rows are 16-byte multiples."""
-    monkeypatch.setenv("SNK_FORCE_KERNEL", "rows")
     for rules, S, D, K, N, steps in (("classic", 4, 14, 4, 60, 150), ("cut", 4, 30, 4, 40, 150), ("adversarial", 3, 10, 4, 50, 150)):
         kw = dict(size=D, n_snakes=S, n_views=K, rules=rules, seed=19)
-        env = sb.SnakeVecEnv(N, **kw)
+        env = sb.SnakeVecEnv(N, debug="force_kernel=rows", **kw)
         assert env.launch_info()["kernel"] == "k_step_rows"
         co = c_oracle.COracle(N, **kw)
         assert np.array_equal(env.reset().cpu().numpy(), co.reset())
@@ -206,17 +205,15 @@ def test_rows_kernel_small_fields(sb, monkeypatch):
             a = c_oracle.gen_actions(co.cfg, t, 5, env.action_space.n)
             _compare_step(env, co, a, "rows %s step %d" % (rules, t), check_state=(t % 10 == 0))
         env.close()
-    monkeypatch.delenv("SNK_FORCE_KERNEL")
 
 
 @pytest.mark.parametrize("kernel", ["tile", "dense"])
-def test_general_kernels_match_oracle(sb, monkeypatch, kernel):
+def test_general_kernels_match_oracle(sb, kernel):
     """The warp-per-env tile kernel and the CTA-per-env dense kernel (used for boards outside the
     lane kernel's class) forced onto small configs."""
-    monkeypatch.setenv("SNK_FORCE_KERNEL", kernel)
     for rules, S, D, N, steps in (("classic", 2, 19, 100, 150), ("adversarial", 3, 10, 100, 200), ("cut", 3, 10, 100, 200)):
         kw = dict(size=D, n_snakes=S, rules=rules, seed=11)
-        env = sb.SnakeVecEnv(N, **kw)
+        env = sb.SnakeVecEnv(N, debug="force_kernel=" + kernel, **kw)
         assert env.launch_info()["kernel"] == "k_step_" + kernel
         co = c_oracle.COracle(N, **kw)
         assert np.array_equal(env.reset().cpu().numpy(), co.reset())
@@ -224,23 +221,21 @@ def test_general_kernels_match_oracle(sb, monkeypatch, kernel):
             a = c_oracle.gen_actions(co.cfg, t, 5, env.action_space.n)
             _compare_step(env, co, a, "%s %s step %d" % (kernel, rules, t), check_state=(t % 10 == 0))
         env.close()
-    monkeypatch.delenv("SNK_FORCE_KERNEL")
 
 
 def test_tile_kernel_golden_replay(sb, monkeypatch):
     """The tile kernel also replays the reference recording of the headline geometry."""
-    monkeypatch.setenv("SNK_FORCE_KERNEL", "tile")
+    monkeypatch.setenv("SNK_DEBUG", "force_kernel=tile")   # the one environment variable snk_create reads
     test_golden_replay(sb, "classic_2x19")
-    monkeypatch.delenv("SNK_FORCE_KERNEL")
+    monkeypatch.delenv("SNK_DEBUG")
 
 
 @pytest.mark.parametrize("rules,S,D", [("adversarial", 32, 40), ("cut", 16, 24)])
-def test_large_field_many_views(sb, monkeypatch, rules, S, D):
+def test_large_field_many_views(sb, rules, S, D):
     """The large-field kernel with 32 views (96-byte pixels, the maximum snake count) and with 16 views on a small board."""
-    monkeypatch.setenv("SNK_FORCE_KERNEL", "rows")
     N = 24
     kw = dict(size=D, n_snakes=S, rules=rules, seed=5)
-    env = sb.SnakeVecEnv(N, **kw)
+    env = sb.SnakeVecEnv(N, debug="force_kernel=rows", **kw)
     assert env.launch_info()["kernel"] == "k_step_rows"
     co = c_oracle.COracle(N, **kw)
     assert np.array_equal(env.reset().cpu().numpy(), co.reset())
@@ -314,33 +309,30 @@ def test_shard_invariance(sb):
 
 
 @pytest.mark.parametrize("variant", ["fused", "ws", "split"])
-def test_lane_kernel_variants_match_oracle(sb, monkeypatch, variant):
+def test_lane_kernel_variants_match_oracle(sb, variant):
     """The alternative forms of the lane path (warp-specialised single kernel; logic + paint as two
     kernels) produce the same bytes as the default fused form."""
-    monkeypatch.setenv("SNK_LANE", variant)
     for rules, S, D, N, steps in (("classic", 2, 19, 1000, 120), ("adversarial", 3, 10, 300, 150), ("cut", 3, 10, 300, 150)):
         kw = dict(size=D, n_snakes=S, rules=rules, seed=13)
-        env = sb.SnakeVecEnv(N, **kw)
+        env = sb.SnakeVecEnv(N, debug="lane=" + variant, **kw)
         co = c_oracle.COracle(N, **kw)
         assert np.array_equal(env.reset().cpu().numpy(), co.reset())
         for t in range(steps):
             a = c_oracle.gen_actions(co.cfg, t, 5, env.action_space.n)
             _compare_step(env, co, a, "%s %s step %d" % (variant, rules, t), check_state=(t % 10 == 0))
         env.close()
-    monkeypatch.delenv("SNK_LANE")
 
 
 @pytest.mark.parametrize("thr,variant", [(1, "fused"), (3, "fused"), (1, "ws"), (2, "split")])
-def test_lane_restore_unpaint_matches_oracle(sb, monkeypatch, thr, variant):
+def test_lane_restore_unpaint_matches_oracle(sb, thr, variant):
     """Un-paint by zero-fill + border redraw (Params::restore_thr) instead of the second chain walk: same bytes.
     thr = 1 restores after almost every image, thr = 3 mixes both forms inside one launch; covers 1 view (3-byte
     pixels, byte-wide border stores), 2 and 3 views, all TE / LPE shapes and long injected bodies."""
-    monkeypatch.setenv("SNK_RESTORE_THR", str(thr))
-    monkeypatch.setenv("SNK_LANE", variant)
+    dbg = "restore_thr=%d,lane=%s" % (thr, variant)
     for rules, S, D, N, steps in (("classic", 2, 19, 1000, 150), ("classic", 1, 10, 500, 100), ("classic", 1, 2, 70, 40),
                                   ("adversarial", 3, 10, 300, 150), ("cut", 3, 14, 300, 150), ("classic", 4, 14, 100, 100)):
         kw = dict(size=D, n_snakes=S, rules=rules, seed=17)
-        env = sb.SnakeVecEnv(N, **kw)
+        env = sb.SnakeVecEnv(N, debug=dbg, **kw)
         assert env.launch_info()["kernel"] == "k_step_lane", (rules, S, D, env.launch_info())
         co = c_oracle.COracle(N, **kw)
         assert np.array_equal(env.reset().cpu().numpy(), co.reset())
@@ -351,7 +343,7 @@ def test_lane_restore_unpaint_matches_oracle(sb, monkeypatch, thr, variant):
     # long bodies: 20-70 segments
     N = 96
     kw = dict(size=19, n_snakes=2, rules="classic", seed=31)
-    env = sb.SnakeVecEnv(N, **kw)
+    env = sb.SnakeVecEnv(N, debug=dbg, **kw)
     co = c_oracle.COracle(N, **kw)
     rng = np.random.RandomState(9)
     blob = helpers.random_long_snake_states(co.lay, co.cfg, rng)
@@ -365,20 +357,16 @@ def test_lane_restore_unpaint_matches_oracle(sb, monkeypatch, thr, variant):
         a[rng.rand(N, 2) < 0.6] = 0
         _compare_step(env, co, a, "restore long step %d" % t, check_state=(t % 20 == 0))
     env.close()
-    monkeypatch.delenv("SNK_RESTORE_THR")
-    monkeypatch.delenv("SNK_LANE")
 
 
 @pytest.mark.parametrize("rules,S,D,kernel", [("classic", 2, 19, None), ("cut", 3, 19, None), ("adversarial", 2, 14, None),
                                                ("classic", 2, 19, "tile"), ("cut", 3, 14, "dense"), ("classic", 4, 30, "rows")])
-def test_injected_long_snakes(sb, monkeypatch, rules, S, D, kernel):
+def test_injected_long_snakes(sb, rules, S, D, kernel):
     """Random long bodies (20-70 segments) loaded through snk_load_state into device and oracle, then
     stepped with actions biased to keep moving: multi-word chain codes, carries, cuts of long bodies."""
-    if kernel:
-        monkeypatch.setenv("SNK_FORCE_KERNEL", kernel)
     N = 96
     kw = dict(size=D, n_snakes=S, rules=rules, seed=31, n_views=4 if kernel == "rows" else None)
-    env = sb.SnakeVecEnv(N, **kw)
+    env = sb.SnakeVecEnv(N, debug=("force_kernel=" + kernel) if kernel else "", **kw)
     co = c_oracle.COracle(N, **kw)
     rng = np.random.RandomState(8)
     blob = helpers.random_long_snake_states(co.lay, co.cfg, rng)
@@ -398,8 +386,6 @@ def test_injected_long_snakes(sb, monkeypatch, rules, S, D, kernel):
         longest = max(longest, int(co.state()["len"].max()))
     assert longest >= 40
     env.close()
-    if kernel:
-        monkeypatch.delenv("SNK_FORCE_KERNEL")
 
 
 def test_cut_equals_classic_without_strikes_full_size(sb):
