@@ -347,7 +347,7 @@ def run_ours(args):
     env = snakes_b200.SnakeVecEnv(N, size=SIZE, n_snakes=N_SNAKES, rules=RULES, seed=0, device=local, env_id_base=rank * N)
     S = env.S
     env.reset()
-    use_comm = world > 1 or args.collective
+    use_comm = (world > 1 or args.collective) and not args.no_collective
     if use_comm:
         env.init_comm()   # from here on every step all-reduces the 8 statistics doubles on a side stream
 
@@ -560,6 +560,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configurations")
     ap.add_argument("--collective", action="store_true", help="run the per-step statistics all-reduce even on one GPU")
+    ap.add_argument("--no-collective", action="store_true", help="A/B: multi-GPU run without the in-loop all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

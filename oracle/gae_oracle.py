@@ -3,8 +3,12 @@
 Restates the reversed loop at the end of the reference's Runner.run
 (/root/reference/src/ppo_multi_agent_new.py:205-218) with the same array dtypes, so that numpy
 performs the same mixed-precision arithmetic: rewards / values float32, done flags bool (so
-`1.0 - flags` is float64), gamma and lam python floats.  The reference function itself needs
-TensorFlow to import, so this oracle is pinned by restatement only (parity unpinned by execution)."""
+`1.0 - flags` is float64), gamma and lam python floats.
+
+Pinned: the reference module needs TensorFlow to import, but its GAE statements are pure numpy; oracle/ref_gae.py lifts
+them out of Runner.run with `ast` and EXECUTES them.  tests/golden/gae_golden.npz holds their outputs (written by
+oracle/make_gae_golden.py in the build container); tests/test_gae_oracle.py checks this restatement against the golden
+file everywhere and against the lifted reference statements wherever /root/reference exists."""
 import numpy as np
 
 

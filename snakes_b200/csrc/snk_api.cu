@@ -83,6 +83,7 @@ struct snk_handle {
   uint64_t step_seq;           // steps launched so far: slot = step_seq & 1
   uint64_t collectives;
   int last_slot;
+  double* d_global_last;       // the all-reduced vector of the most recent step (a slot of d_global or of a graph)
   snk_graph* rollout_cache;    // the graph of the last snk_rollout call (re-launched when the arguments repeat)
   std::string debug;
 };
@@ -218,6 +219,7 @@ struct snk_graph {
   // arguments it was captured with (snk_rollout's cache key)
   const int8_t* d_actions; int32_t n_batches; uint8_t* d_obs; float* d_reward; uint8_t* d_done; uint32_t flags;
   uint8_t* obs_target; bool with_comm;
+  double* d_slots;  // with a communicator: [T] snapshot slots + [T] all-reduced slots, one pair per step (no reuse inside a launch)
 };
 
 extern "C" int snk_graph_destroy(snk_graph* g) {
@@ -225,6 +227,9 @@ extern "C" int snk_graph_destroy(snk_graph* g) {
   if (g->h && g->h->rollout_cache == g) g->h->rollout_cache = nullptr;
   if (g->exec) cudaGraphExecDestroy(g->exec);
   if (g->graph) cudaGraphDestroy(g->graph);
+  if (g->h && g->h->d_global_last >= g->d_slots && g->d_slots && g->h->d_global_last < g->d_slots + 2 * (size_t)g->T * SNK_NSTATS)
+    g->h->d_global_last = nullptr;
+  if (g->d_slots) cudaFree(g->d_slots);
   delete g;
   return SNK_OK;
 }
@@ -273,6 +278,7 @@ extern "C" int snk_create_ex(const snk_config* cfg, const char* debug_opts, snk_
   h->d_tape_vals = h->d_tape_bounds = nullptr; h->d_tape_off = nullptr;
   h->comm = nullptr; h->comm_ranks = 1; h->comm_rank = 0; h->side = nullptr; h->cap_stream = nullptr;
   h->d_snap = h->d_global = nullptr; h->step_seq = 0; h->collectives = 0; h->last_slot = 0; h->rollout_cache = nullptr;
+  h->d_global_last = nullptr;
   for (int i = 0; i < 2; ++i) { h->ev_step[i] = h->ev_red[i] = h->cev_step[i] = h->cev_red[i] = nullptr; h->ev_red_valid[i] = false; }
   h->debug = debug_opts ? debug_opts : "";
   const std::string& dbg = h->debug;
@@ -493,8 +499,15 @@ struct RolloutSlot {  // per-step output redirection of a rollout graph
 
 // One step (or reset / re-encode) on `stream`.  `capturing`: the call is being recorded into a CUDA graph (snk_graph_create);
 // the per-step statistics all-reduce then forks onto the side stream with capture-time events.
+struct CaptureCtx {  // a step being recorded into a CUDA graph
+  int step;
+  double* slots;     // the graph's own [T] snapshot + [T] result slots (NULL without a communicator)
+  int T;
+};
+
 static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_t* d_mask, cudaStream_t stream,
-                  const RolloutSlot* slot = nullptr, bool capturing = false, int cap_step = 0) {
+                  const RolloutSlot* slot = nullptr, const CaptureCtx* cap = nullptr) {
+  const bool capturing = cap != nullptr;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   Params p = h->p;
   uint8_t* obs_user = h->d_obs_user;
@@ -511,25 +524,33 @@ static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_
   if (p.rng_mode == SNK_RNG_TAPE && !p.tape_vals) return fail(SNK_EINVAL, "rng_mode is TAPE but no tape was set");
   const bool reduce = h->comm && mode == MODE_STEP;
   int sl = 0;
+  double* snap = nullptr;
+  double* glob = nullptr;
   if (reduce) {
-    sl = capturing ? (cap_step & 1) : (int)(h->step_seq & 1);
-    p.snap = h->d_snap + sl * SNK_NSTATS;
-    // the all-reduce that last read this snapshot slot (two steps ago) must be done before the kernel rewrites it
-    if (capturing) { if (cap_step >= 2) CUDA_TRY(cudaStreamWaitEvent(stream, h->cev_red[sl], 0)); }
-    else if (h->ev_red_valid[sl]) CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_red[sl], 0));
-  } else {
-    p.snap = nullptr;
+    if (capturing) {
+      // inside a graph every step has its own pair of slots: nothing is reused within a launch, so a step kernel depends
+      // on its predecessor alone (the programmatic edge) and the all-reduces form an independent side branch
+      snap = cap->slots + (size_t)cap->step * SNK_NSTATS;
+      glob = cap->slots + (size_t)(cap->T + cap->step) * SNK_NSTATS;
+    } else {
+      sl = (int)(h->step_seq & 1);
+      snap = h->d_snap + sl * SNK_NSTATS;
+      glob = h->d_global + sl * SNK_NSTATS;
+      // the all-reduce that last read this snapshot slot (two steps ago) must be done before the kernel rewrites it
+      if (h->ev_red_valid[sl]) CUDA_TRY(cudaStreamWaitEvent(stream, h->ev_red[sl], 0));
+    }
   }
+  p.snap = snap;
   CUDA_TRY(snk_launch_step(p, h->cfg.rules, h->plan, stream));
   h->launches += (h->plan.split && mode != MODE_OBSERVE) ? 2 : 1;
   if (reduce) {
     // side stream: all-reduce this step's snapshot while the next step runs; its result is read one step late
-    cudaEvent_t es = capturing ? h->cev_step[sl] : h->ev_step[sl], er = capturing ? h->cev_red[sl] : h->ev_red[sl];
+    cudaEvent_t es = capturing ? h->cev_step[0] : h->ev_step[sl], er = capturing ? h->cev_red[0] : h->ev_red[sl];
     CUDA_TRY(cudaEventRecord(es, stream));
     CUDA_TRY(cudaStreamWaitEvent(h->side, es, 0));
-    NCCL_TRY(g_nccl.AllReduce(h->d_snap + sl * SNK_NSTATS, h->d_global + sl * SNK_NSTATS, SNK_NSTATS, kNcclFloat64, kNcclSum, h->comm, h->side));
+    NCCL_TRY(g_nccl.AllReduce(snap, glob, SNK_NSTATS, kNcclFloat64, kNcclSum, h->comm, h->side));
     CUDA_TRY(cudaEventRecord(er, h->side));
-    if (!capturing) { h->ev_red_valid[sl] = true; h->step_seq++; h->collectives++; h->last_slot = sl; }
+    if (!capturing) { h->ev_red_valid[sl] = true; h->step_seq++; h->collectives++; h->last_slot = sl; h->d_global_last = glob; }
   }
   if (h->cfg.obs_mode == SNK_OBS_ATARI84) {
     CUDA_TRY(snk_launch_upscale84(p.obs, obs_user, p.N, p.V, p.C, h->n_sm, stream));
@@ -571,7 +592,14 @@ static int graph_create_impl(snk_handle* h, const int8_t* d_actions, int32_t n_b
   snk_graph* g = new snk_graph();
   g->h = h; g->graph = nullptr; g->exec = nullptr; g->T = T;
   g->d_actions = d_actions; g->n_batches = n_batches; g->d_obs = d_obs; g->d_reward = d_reward; g->d_done = d_done; g->flags = flags;
-  g->obs_target = h->d_obs_user; g->with_comm = h->comm != nullptr;
+  g->obs_target = h->d_obs_user; g->with_comm = h->comm != nullptr; g->d_slots = nullptr;
+  if (h->comm) {
+    const size_t bytes = sizeof(double) * 2 * (size_t)T * SNK_NSTATS;
+    if (cudaMalloc(&g->d_slots, bytes) != cudaSuccess || cudaMemset(g->d_slots, 0, bytes) != cudaSuccess) {
+      delete g;
+      return fail(SNK_ENOMEM, "cudaMalloc of the graph's statistics slots");
+    }
+  }
   const uint64_t l0 = h->launches;
   cudaStream_t s = h->cap_stream;
   cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
@@ -587,11 +615,11 @@ static int graph_create_impl(snk_handle* h, const int8_t* d_actions, int32_t n_b
         rc = fail(SNK_ECUDA, "capture: scripted policy kernel");
       h->launches++;
     }
-    if (rc == SNK_OK) rc = launch(h, MODE_STEP, d_actions + (size_t)(t % n_batches) * p.N * p.S, nullptr, s, &slot, true, t);
+    const CaptureCtx cap = {t, g->d_slots, T};
+    if (rc == SNK_OK) rc = launch(h, MODE_STEP, d_actions + (size_t)(t % n_batches) * p.N * p.S, nullptr, s, &slot, &cap);
   }
-  if (rc == SNK_OK && h->comm) {  // join the side stream's last two all-reduces back into the origin stream
-    for (int t = T - 2 < 0 ? 0 : T - 2; t < T; ++t)
-      if (cudaStreamWaitEvent(s, h->cev_red[t & 1], 0) != cudaSuccess) rc = fail(SNK_ECUDA, "cudaStreamWaitEvent (capture join)");
+  if (rc == SNK_OK && h->comm) {  // join the side branch (its last all-reduce) back into the origin stream
+    if (cudaStreamWaitEvent(s, h->cev_red[0], 0) != cudaSuccess) rc = fail(SNK_ECUDA, "cudaStreamWaitEvent (capture join)");
   }
   if (rc == SNK_OK && d_obs && (flags & SNK_GRAPH_SYNC_BACK)) {
     // leave the handle's own buffers as after T calls of snk_step
@@ -640,8 +668,7 @@ extern "C" int snk_graph_launch(snk_graph* g, void* stream) {
   h->launches += g->launches_per_run;
   if (g->with_comm) {
     h->collectives += g->collectives_per_run;
-    h->last_slot = (g->T - 1) & 1;
-    h->step_seq = (uint64_t)g->T;  // the next eager step continues the slot alternation
+    h->d_global_last = g->d_slots + (size_t)(2 * g->T - 1) * SNK_NSTATS;  // the result slot of the graph's last step
     h->ev_red_valid[0] = h->ev_red_valid[1] = false;  // the graph joined its own all-reduces; stream order covers them
   }
   return SNK_OK;
@@ -935,7 +962,8 @@ extern "C" int snk_get_stats_global(snk_handle* h, double* h_stats, void* stream
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   int rc = join_side(h, s);
   if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(h_stats, h->d_global + h->last_slot * SNK_NSTATS, sizeof(double) * SNK_NSTATS, cudaMemcpyDeviceToHost, s));
+  if (!h->d_global_last) return snk_get_stats(h, h_stats, stream);  // no step since snk_comm_init (or its graph is gone)
+  CUDA_TRY(cudaMemcpyAsync(h_stats, h->d_global_last, sizeof(double) * SNK_NSTATS, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return SNK_OK;
 }

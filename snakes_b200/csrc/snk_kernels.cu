@@ -926,6 +926,7 @@ __global__ void __launch_bounds__(128) k_scripted_actions(const Params p, int8_t
 #pragma unroll
   for (int s = 0; s < S; ++s)
     chain_walk(env.head[s], env.len[s], env.c0[s], p.chain + (e * S + s) * p.CW, V, [&](int, int pid) { occ[pid >> 5] |= 1u << (pid & 31); });
+  u32 packed = 0;
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     int best = 0;
@@ -948,7 +949,13 @@ __global__ void __launch_bounds__(128) k_scripted_actions(const Params p, int8_t
         }
       }
     }
-    actions[e * S + s] = (int8_t)best;
+    packed |= (u32)best << (8 * s);
+  }
+  if (S == 2) *reinterpret_cast<u16*>(actions + e * S) = (u16)packed;
+  else if (S == 4) *reinterpret_cast<u32*>(actions + e * S) = packed;
+  else {
+#pragma unroll
+    for (int s = 0; s < S; ++s) actions[e * S + s] = (int8_t)(packed >> (8 * s));
   }
 }
 
