@@ -349,7 +349,7 @@ def run_ours(args):
     env.reset()
     use_comm = (world > 1 or args.collective) and not args.no_collective
     if use_comm:
-        env.init_comm()   # from here on every step all-reduces the 8 statistics doubles on a side stream
+        env.init_comm(mode=args.comm)   # from here on every step sums the 8 statistics doubles over all ranks
 
     # ---- parity of THIS rank's envs on THIS handle, before anything is timed
     ok, n_checked, n_steps = rank_parity(env, rank)
@@ -385,13 +385,37 @@ def run_ours(args):
     stats_local = env.stats(reduce=False)
     collective = None
     if use_comm:
-        stats = env.stats_global()  # what the in-loop all-reduce delivered (all K steps joined by the graph)
+        barrier()                   # every rank has finished its K steps: all pushes / all-reduces have landed
+        stats = env.stats_global()  # what the in-loop reduction delivered
         check = env.stats(reduce=True)  # the same sums through torch.distributed, after the fact
-        collective = {"bytes": 8 * 8, "per": "step", "count": env.comm_info()["allreduces"] - c0, "inside_timed_region": True,
-                      "us": env.comm_latency_us(200), "ranks": env.comm_info()["ranks"], "nccl_version": env.comm_info()["nccl_version"],
-                      "how": "raw ncclAllReduce(8 x f64, sum) issued by libsnk.so on a high-priority side stream, one graph node per "
-                             "step, overlapped with the next step and read one step late (snk_comm_init / snk_get_stats_global)",
+        info = env.comm_info()
+        collective = {"bytes": 8 * 8, "per": "step", "count": info["allreduces"] - c0, "inside_timed_region": True,
+                      "ranks": info["ranks"], "mode": args.comm,
                       "matches_torch_all_reduce": all(abs(stats[k] - check[k]) < 1e-6 for k in stats)}
+        if args.comm == "nccl":
+            collective["us"] = env.comm_latency_us(200)
+            collective["nccl_version"] = info["nccl_version"]
+            collective["how"] = ("raw ncclAllReduce(8 x f64, sum) issued by libsnk.so on a high-priority side stream, one graph node "
+                                 "per step, overlapped with the next step and read one step late (snk_comm_init / snk_get_stats_global)")
+        else:
+            collective["how"] = ("fused into the step kernel: its first CTA stores the rank's 8 running sums (as of the previous step) "
+                                 "into every peer's inbox over NVLink (cudaIpc peer memory, posted 8-byte stores, no fence, no "
+                                 "rendezvous); a reader adds its own sums and the peers' latest pushes "
+                                 "(snk_peer_connect / snk_get_stats_global)")
+        # what the reduction costs: the same K steps with it switched off, outside the headline timing
+        env.comm_enable(False)
+        g_off = env.make_graph(acts, T=K)
+        g_off.launch()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(); g_off.launch(); f1.record()
+        barrier()
+        ms_off = max_over_ranks(f0.elapsed_time(f1))
+        g_off.close()
+        env.comm_enable(True)
+        collective["us_per_step_with"] = ms / K * 1e3
+        collective["us_per_step_without"] = ms_off / K * 1e3
+        env.reset_stats()
     else:
         stats = stats_local
     g_warm.close(); g_main.close()
@@ -561,6 +585,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configurations")
     ap.add_argument("--collective", action="store_true", help="run the per-step statistics all-reduce even on one GPU")
     ap.add_argument("--no-collective", action="store_true", help="A/B: multi-GPU run without the in-loop all-reduce")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="form of the per-step statistics reduction: fused peer-memory pushes (default) or ncclAllReduce on a side stream")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -181,6 +181,15 @@ int snk_host_free(snk_handle* h, void* ptr);
  * NULL restores the internal buffer.  Must be 16-byte aligned. */
 int snk_set_obs_target(snk_handle* h, uint8_t* d_obs, size_t bytes);
 
+/* The learner's rollout keeps the MAIN snake's view alone (ppo_multi_agent_new.py:181 `mb_obs.append(self.main_obs)`,
+ * with main_obs = obs[..., 0:3], :162); the opponents' views are needed once, for their action, and then dropped.
+ * With a main-view target set, every snk_step / snk_reset additionally writes view 0 of all envs, packed as
+ * [N][H][W][3], into d_main (slot t of a [nsteps][N][H][W][3] buffer) while all K views stay in the handle's own,
+ * transient observation buffer.  NULL switches it off.  (A gather kernel behind the step kernel: the interleaved
+ * [N][H][W][3K] layout of the reference is what the step kernel streams out; see DESIGN.md section 4.9 for why a planar
+ * store was not adopted.) */
+int snk_set_main_view_target(snk_handle* h, uint8_t* d_main, size_t bytes);
+
 /* T steps back to back into a caller-owned rollout buffer, no host round trip: step t reads
  * d_actions[t] (int8 [T][N][S]) and writes its observations into d_obs[t] ([T][N][H][W][3K]), its
  * rewards into d_reward[t] (float [T][N]) and its dones into d_done[t] (uint8 [T][N]).  Replaces the
@@ -250,6 +259,20 @@ int snk_check_errors(snk_handle* h, uint32_t* flags, void* stream);
  *   snk_comm_init       collective over all ranks; NCCL is bound at run time (dlopen of libnccl.so.2), no link dependency.
  *   snk_get_stats_global  sums over all ranks as of the last completed reduction (synchronises `stream`); without a
  *                       communicator it equals snk_get_stats. */
+/* The same reduction WITHOUT a collective library and without a kernel of its own -- the default of the Python layer.
+ * Every rank exports a small inbox (cudaIpc) and maps its peers' inboxes (snk_peer_connect, after the caller has gathered
+ * the 64-byte handles of all ranks in rank order over any channel).  From then on the FIRST CTA of every step kernel
+ * stores the rank's running sums -- complete as of the previous step -- into its slot of every peer's inbox: eight
+ * aligned 8-byte stores per peer over NVLink / NVSwitch, posted, draining while the CTA steps its envs.  Every statistic
+ * is a monotonic sum and an aligned 8-byte store is one transaction, so there are no fences, no versions and no
+ * rendezvous: a rank never waits for another, and compute step and exchange are one kernel.  snk_get_stats_global pushes
+ * the rank's final sums and returns own sums + the peers' latest pushes: the global statistics as of about one step ago,
+ * exact once every rank has made that call after its last step (call it, barrier, call it again).  Ranks must be
+ * processes of one node with peer access between their GPUs; at most 16.
+ * snk_comm_enable(h, 0) switches the per-step reduction of either form off (A/B measurements), 1 on again. */
+int snk_peer_export(snk_handle* h, uint8_t* out64);
+int snk_peer_connect(snk_handle* h, const uint8_t* handles /*[n_ranks][64]*/, int32_t n_ranks, int32_t rank);
+int snk_comm_enable(snk_handle* h, int32_t on);
 int snk_comm_unique_id(uint8_t* out128);
 int snk_comm_init(snk_handle* h, const uint8_t* id128, int32_t n_ranks, int32_t rank);
 int snk_get_stats_global(snk_handle* h, double* h_stats /*[SNK_NSTATS]*/, void* stream);

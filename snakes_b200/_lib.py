@@ -62,6 +62,7 @@ _SIGNATURES = {
     "snk_graph_destroy": (C.c_int, [C.c_void_p]),
     "snk_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_set_obs_target": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "snk_set_main_view_target": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "snk_set_draw_tape": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_state_layout_of": (C.c_int, [C.POINTER(SnkConfig), C.POINTER(SnkStateLayout)]),
     "snk_dump_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -70,6 +71,9 @@ _SIGNATURES = {
     "snk_get_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_reset_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "snk_check_errors": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]),
+    "snk_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "snk_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "snk_comm_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "snk_comm_unique_id": (C.c_int, [C.c_void_p]),
     "snk_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "snk_get_stats_global": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

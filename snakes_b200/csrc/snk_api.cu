@@ -41,12 +41,21 @@ struct NcclApi {
   void* so;
   int (*GetUniqueId)(ncclUniqueId*);
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  int (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, void* /*ncclConfig_t*/);
   int (*CommDestroy)(ncclComm_t);
   int (*AllReduce)(const void*, void*, size_t, int /*ncclDataType_t*/, int /*ncclRedOp_t*/, ncclComm_t, cudaStream_t);
   const char* (*GetErrorString)(int);
   int (*GetVersion)(int*);
 };
 static const int kNcclFloat64 = 8, kNcclSum = 0;  // nccl.h: ncclFloat64 = 8, ncclSum = 0 (stable since NCCL 2.0)
+// ncclConfig_t as of NCCL 2.18 (nccl.h: size / magic / version head the struct precisely so that a caller built against an
+// older layout keeps working: fields beyond `size` take their defaults)
+struct NcclConfig218 {
+  size_t size; unsigned magic, version;
+  int blocking, cgaClusterSize, minCTAs, maxCTAs;
+  const char* netName;
+  int splitShare;
+};
 
 struct snk_handle {
   snk_config cfg;
@@ -57,6 +66,7 @@ struct snk_handle {
   uint8_t* d_obs_own;     // native observations (the step kernels' output)
   uint8_t* d_obs84_own;   // obs_mode atari84: the 84x84 images handed to the caller
   uint8_t* d_obs_user;    // what snk_get_buffers reports: own buffer or the caller's target
+  uint8_t* d_main_target; // snk_set_main_view_target: view 0 of every step, packed [N][H][W][3] (NULL = off)
   size_t obs_out_env_bytes;
   int8_t* d_actions_own;
   uint8_t* d_blob;  // staging for dump / load
@@ -84,6 +94,11 @@ struct snk_handle {
   uint64_t collectives;
   int last_slot;
   double* d_global_last;       // the all-reduced vector of the most recent step (a slot of d_global or of a graph)
+  // peer-memory form (snk_peer_export / snk_peer_connect)
+  uint8_t* d_inbox;            // this rank's inbox (cudaMalloc, exported through cudaIpc)
+  void* peer_mapped[SNK_MAX_PEERS];  // the peers' inboxes as opened in this process
+  PeerArgs peer;               // ranks == 0: peer form not connected
+  bool reduce_enabled;         // snk_comm_enable: A/B switch of the per-step reduction
   snk_graph* rollout_cache;    // the graph of the last snk_rollout call (re-launched when the arguments repeat)
   std::string debug;
 };
@@ -195,6 +210,7 @@ static int nccl_load() {
   a.so = so;
   *(void**)&a.GetUniqueId = dlsym(so, "ncclGetUniqueId");
   *(void**)&a.CommInitRank = dlsym(so, "ncclCommInitRank");
+  *(void**)&a.CommInitRankConfig = dlsym(so, "ncclCommInitRankConfig");
   *(void**)&a.CommDestroy = dlsym(so, "ncclCommDestroy");
   *(void**)&a.AllReduce = dlsym(so, "ncclAllReduce");
   *(void**)&a.GetErrorString = dlsym(so, "ncclGetErrorString");
@@ -218,7 +234,7 @@ struct snk_graph {
   uint64_t launches_per_run, collectives_per_run;
   // arguments it was captured with (snk_rollout's cache key)
   const int8_t* d_actions; int32_t n_batches; uint8_t* d_obs; float* d_reward; uint8_t* d_done; uint32_t flags;
-  uint8_t* obs_target; bool with_comm;
+  uint8_t* obs_target; bool with_comm, with_push;
   double* d_slots;  // with a communicator: [T] snapshot slots + [T] all-reduced slots, one pair per step (no reuse inside a launch)
 };
 
@@ -240,6 +256,8 @@ extern "C" int snk_destroy(snk_handle* h) {
   cudaDeviceSynchronize();
   if (h->rollout_cache) snk_graph_destroy(h->rollout_cache);
   if (h->comm && g_nccl.so) g_nccl.CommDestroy(h->comm);
+  for (int i = 0; i < SNK_MAX_PEERS; ++i)
+    if (h->peer_mapped[i]) cudaIpcCloseMemHandle(h->peer_mapped[i]);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_step[i]) cudaEventDestroy(h->ev_step[i]);
     if (h->ev_red[i]) cudaEventDestroy(h->ev_red[i]);
@@ -274,11 +292,14 @@ extern "C" int snk_create_ex(const snk_config* cfg, const char* debug_opts, snk_
   if (h->cfg.n_views == 0) h->cfg.n_views = cfg->n_snakes;
   if (h->cfg.max_steps == 0) h->cfg.max_steps = 2000;
   h->launches = 0;
+  h->d_main_target = nullptr;
   h->d_obs_own = nullptr; h->d_actions_own = nullptr; h->d_blob = nullptr; h->blob_bytes = 0; h->d_views = nullptr; h->views_bytes = 0;
   h->d_tape_vals = h->d_tape_bounds = nullptr; h->d_tape_off = nullptr;
   h->comm = nullptr; h->comm_ranks = 1; h->comm_rank = 0; h->side = nullptr; h->cap_stream = nullptr;
   h->d_snap = h->d_global = nullptr; h->step_seq = 0; h->collectives = 0; h->last_slot = 0; h->rollout_cache = nullptr;
   h->d_global_last = nullptr;
+  h->d_inbox = nullptr; memset(&h->peer, 0, sizeof(h->peer)); h->reduce_enabled = true;
+  for (int i = 0; i < SNK_MAX_PEERS; ++i) h->peer_mapped[i] = nullptr;
   for (int i = 0; i < 2; ++i) { h->ev_step[i] = h->ev_red[i] = h->cev_step[i] = h->cev_red[i] = nullptr; h->ev_red_valid[i] = false; }
   h->debug = debug_opts ? debug_opts : "";
   const std::string& dbg = h->debug;
@@ -522,7 +543,9 @@ static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_
   p.mode = mode; p.actions = d_actions; p.mask = d_mask;
   p.tape_vals = h->d_tape_vals; p.tape_bounds = h->d_tape_bounds; p.tape_off = h->d_tape_off;
   if (p.rng_mode == SNK_RNG_TAPE && !p.tape_vals) return fail(SNK_EINVAL, "rng_mode is TAPE but no tape was set");
-  const bool reduce = h->comm && mode == MODE_STEP;
+  const bool reduce = h->comm && h->reduce_enabled && mode == MODE_STEP;   // NCCL form: snapshot + all-reduce on the side stream
+  const bool push = h->peer.ranks > 0 && h->reduce_enabled && mode == MODE_STEP;  // peer form: the step kernel's first CTA pushes
+  if (push) p.peer = h->peer;
   int sl = 0;
   double* snap = nullptr;
   double* glob = nullptr;
@@ -552,8 +575,14 @@ static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_
     CUDA_TRY(cudaEventRecord(er, h->side));
     if (!capturing) { h->ev_red_valid[sl] = true; h->step_seq++; h->collectives++; h->last_slot = sl; h->d_global_last = glob; }
   }
+  if (push && !capturing) h->collectives++;
   if (h->cfg.obs_mode == SNK_OBS_ATARI84) {
     CUDA_TRY(snk_launch_upscale84(p.obs, obs_user, p.N, p.V, p.C, h->n_sm, stream));
+    h->launches++;
+  }
+  if (h->d_main_target && !capturing) {  // the main snake's view alone, packed, for the learner's rollout slot
+    const size_t px = (size_t)p.N * (h->obs_out_env_bytes / (size_t)p.C);
+    CUDA_TRY(snk_launch_extract_views(obs_user, h->d_main_target, (long long)px, p.C, 1, stream));
     h->launches++;
   }
   return SNK_OK;
@@ -592,8 +621,10 @@ static int graph_create_impl(snk_handle* h, const int8_t* d_actions, int32_t n_b
   snk_graph* g = new snk_graph();
   g->h = h; g->graph = nullptr; g->exec = nullptr; g->T = T;
   g->d_actions = d_actions; g->n_batches = n_batches; g->d_obs = d_obs; g->d_reward = d_reward; g->d_done = d_done; g->flags = flags;
-  g->obs_target = h->d_obs_user; g->with_comm = h->comm != nullptr; g->d_slots = nullptr;
-  if (h->comm) {
+  const bool reducing = h->comm && h->reduce_enabled;                   // NCCL form: per-step slots and a forked branch
+  const bool pushing = h->peer.ranks > 0 && h->reduce_enabled;          // peer form: nothing beside the step kernels
+  g->obs_target = h->d_obs_user; g->with_comm = reducing; g->with_push = pushing; g->d_slots = nullptr;
+  if (reducing) {
     const size_t bytes = sizeof(double) * 2 * (size_t)T * SNK_NSTATS;
     if (cudaMalloc(&g->d_slots, bytes) != cudaSuccess || cudaMemset(g->d_slots, 0, bytes) != cudaSuccess) {
       delete g;
@@ -618,7 +649,7 @@ static int graph_create_impl(snk_handle* h, const int8_t* d_actions, int32_t n_b
     const CaptureCtx cap = {t, g->d_slots, T};
     if (rc == SNK_OK) rc = launch(h, MODE_STEP, d_actions + (size_t)(t % n_batches) * p.N * p.S, nullptr, s, &slot, &cap);
   }
-  if (rc == SNK_OK && h->comm) {  // join the side branch (its last all-reduce) back into the origin stream
+  if (rc == SNK_OK && reducing) {  // join the side branch (its last all-reduce) back into the origin stream
     if (cudaStreamWaitEvent(s, h->cev_red[0], 0) != cudaSuccess) rc = fail(SNK_ECUDA, "cudaStreamWaitEvent (capture join)");
   }
   if (rc == SNK_OK && d_obs && (flags & SNK_GRAPH_SYNC_BACK)) {
@@ -633,7 +664,7 @@ static int graph_create_impl(snk_handle* h, const int8_t* d_actions, int32_t n_b
   ce = cudaStreamEndCapture(s, &g->graph);
   g->launches_per_run = h->launches - l0;
   h->launches = l0;  // nothing ran yet
-  g->collectives_per_run = h->comm ? (uint64_t)T : 0;
+  g->collectives_per_run = (reducing || pushing) ? (uint64_t)T : 0;
   if (rc != SNK_OK) { snk_graph_destroy(g); return rc; }
   if (ce != cudaSuccess) { snk_graph_destroy(g); return fail(SNK_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce)); }
   ce = cudaGraphInstantiate(&g->exec, g->graph, 0);
@@ -666,8 +697,8 @@ extern "C" int snk_graph_launch(snk_graph* g, void* stream) {
   }
   CUDA_TRY(cudaGraphLaunch(g->exec, s));
   h->launches += g->launches_per_run;
+  h->collectives += g->collectives_per_run;
   if (g->with_comm) {
-    h->collectives += g->collectives_per_run;
     h->d_global_last = g->d_slots + (size_t)(2 * g->T - 1) * SNK_NSTATS;  // the result slot of the graph's last step
     h->ev_red_valid[0] = h->ev_red_valid[1] = false;  // the graph joined its own all-reduces; stream order covers them
   }
@@ -680,7 +711,8 @@ extern "C" int snk_rollout(snk_handle* h, const int8_t* d_actions, int32_t T, ui
   snk_graph* g = h->rollout_cache;
   const uint32_t flags = SNK_GRAPH_SYNC_BACK;
   if (g && !(g->d_actions == d_actions && g->n_batches == T && g->T == T && g->d_obs == d_obs && g->d_reward == d_reward &&
-             g->d_done == d_done && g->flags == flags && g->obs_target == h->d_obs_user && g->with_comm == (h->comm != nullptr))) {
+             g->d_done == d_done && g->flags == flags && g->obs_target == h->d_obs_user &&
+             g->with_comm == (h->comm && h->reduce_enabled) && g->with_push == (h->peer.ranks > 0 && h->reduce_enabled))) {
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));  // the cached graph may still be running
     snk_graph_destroy(g);
     g = nullptr;
@@ -814,6 +846,15 @@ extern "C" int snk_set_obs_target(snk_handle* h, uint8_t* d_obs, size_t bytes) {
   return SNK_OK;
 }
 
+extern "C" int snk_set_main_view_target(snk_handle* h, uint8_t* d_main, size_t bytes) {
+  if (!h) return fail(SNK_EINVAL, "handle is NULL");
+  if (!d_main) { h->d_main_target = nullptr; return SNK_OK; }
+  const size_t need = (size_t)h->p.N * (h->obs_out_env_bytes / (size_t)h->p.C) * 3;
+  if (bytes < need) return fail(SNK_EINVAL, "main-view target too small: %zu < %zu", bytes, need);
+  h->d_main_target = d_main;
+  return SNK_OK;
+}
+
 extern "C" int snk_set_draw_tape(snk_handle* h, const uint32_t* h_vals, const uint32_t* h_bounds, const uint64_t* h_offsets) {
   if (!h || !h_vals || !h_offsets) return fail(SNK_EINVAL, "NULL argument");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -926,16 +967,10 @@ extern "C" int snk_comm_unique_id(uint8_t* out128) {
   return SNK_OK;
 }
 
-extern "C" int snk_comm_init(snk_handle* h, const uint8_t* id128, int32_t n_ranks, int32_t rank) {
-  if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(SNK_EINVAL, "bad argument");
-  if (h->comm) return fail(SNK_EINVAL, "communicator already initialised");
-  int rc = nccl_load();
-  if (rc) return rc;
-  CUDA_TRY(cudaSetDevice(h->cfg.device));
-  ncclUniqueId id;
-  memcpy(&id, id128, sizeof(id));
-  ncclComm_t comm = nullptr;
-  NCCL_TRY(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+// what both forms of the per-step reduction share: the high-priority side stream, the fork / join events (eager and
+// capture-time sets) and the two eager snapshot / result slots
+static int ensure_side(snk_handle* h) {
+  if (h->side) return SNK_OK;
   int lo = 0, hi = 0;
   CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   CUDA_TRY(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
@@ -945,8 +980,33 @@ extern "C" int snk_comm_init(snk_handle* h, const uint8_t* id128, int32_t n_rank
     CUDA_TRY(cudaEventCreateWithFlags(&h->cev_step[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&h->cev_red[i], cudaEventDisableTiming));
   }
+  int rc;
   if ((rc = dev_alloc(h, &h->d_snap, (size_t)2 * SNK_NSTATS, true))) return rc;
   if ((rc = dev_alloc(h, &h->d_global, (size_t)2 * SNK_NSTATS, true))) return rc;
+  return SNK_OK;
+}
+
+extern "C" int snk_comm_init(snk_handle* h, const uint8_t* id128, int32_t n_ranks, int32_t rank) {
+  if (!h || !id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(SNK_EINVAL, "bad argument");
+  if (h->comm || h->peer.ranks > 0) return fail(SNK_EINVAL, "a reduction is already set up on this handle");
+  int rc = nccl_load();
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  if (g_nccl.CommInitRankConfig) {
+    // a 64-byte all-reduce needs ONE CTA: every further channel is a CTA that has to wait for room on an SM the step
+    // kernel fills (measured at 2 GPUs: the default cost 2 us per step, 3 %)
+    NcclConfig218 cfg;
+    cfg.size = sizeof(cfg); cfg.magic = 0xcafebeefu; cfg.version = 21800;
+    const int undef = (int)0x80000000;  // NCCL_CONFIG_UNDEF_INT
+    cfg.blocking = undef; cfg.cgaClusterSize = undef; cfg.minCTAs = 1; cfg.maxCTAs = 1; cfg.netName = nullptr; cfg.splitShare = undef;
+    NCCL_TRY(g_nccl.CommInitRankConfig(&comm, n_ranks, id, rank, &cfg));
+  } else {
+    NCCL_TRY(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+  }
+  if ((rc = ensure_side(h))) return rc;
   // one eager all-reduce now: NCCL sets its connections up on first use, which must not happen inside a stream capture
   NCCL_TRY(g_nccl.AllReduce(h->d_snap, h->d_global, SNK_NSTATS, kNcclFloat64, kNcclSum, comm, h->side));
   CUDA_TRY(cudaStreamSynchronize(h->side));
@@ -955,8 +1015,68 @@ extern "C" int snk_comm_init(snk_handle* h, const uint8_t* id128, int32_t n_rank
   return SNK_OK;
 }
 
+extern "C" int snk_peer_export(snk_handle* h, uint8_t* out64) {
+  if (!h || !out64) return fail(SNK_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (!h->d_inbox) {
+    const size_t bytes = (size_t)SNK_MAX_PEERS * SNK_INBOX_STRIDE;
+    void* ptr = nullptr;
+    cudaError_t e = cudaMalloc(&ptr, bytes);  // its own allocation: cudaIpc exports whole allocations
+    if (e != cudaSuccess) return fail(SNK_ENOMEM, "cudaMalloc(inbox): %s", cudaGetErrorString(e));
+    h->allocs.push_back(ptr);
+    CUDA_TRY(cudaMemset(ptr, 0, bytes));
+    h->d_inbox = (uint8_t*)ptr;
+  }
+  cudaIpcMemHandle_t ipc;
+  static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->d_inbox));
+  memcpy(out64, &ipc, sizeof(ipc));
+  return SNK_OK;
+}
+
+extern "C" int snk_peer_connect(snk_handle* h, const uint8_t* handles, int32_t n_ranks, int32_t rank) {
+  if (!h || !handles || n_ranks < 1 || n_ranks > SNK_MAX_PEERS || rank < 0 || rank >= n_ranks) return fail(SNK_EINVAL, "bad argument");
+  if (!h->d_inbox) return fail(SNK_EINVAL, "snk_peer_export first");
+  if (h->peer.ranks > 0 || h->comm) return fail(SNK_EINVAL, "a reduction is already set up on this handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  PeerArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int g = 0; g < n_ranks; ++g) {
+    if (g == rank) { a.inbox[g] = h->d_inbox; continue; }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, handles + (size_t)g * sizeof(ipc), sizeof(ipc));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(SNK_ECOMM, "cudaIpcOpenMemHandle(rank %d): %s", g, cudaGetErrorString(e));
+    h->peer_mapped[g] = ptr;
+    a.inbox[g] = (uint8_t*)ptr;
+  }
+  int rc;
+  if (!h->d_global && (rc = dev_alloc(h, &h->d_global, (size_t)2 * SNK_NSTATS, true))) return rc;
+  a.ranks = n_ranks; a.rank = rank;
+  h->peer = a;
+  h->comm_ranks = n_ranks; h->comm_rank = rank;
+  if (h->rollout_cache) snk_graph_destroy(h->rollout_cache);  // captured without the exchange
+  return SNK_OK;
+}
+
+extern "C" int snk_comm_enable(snk_handle* h, int32_t on) {
+  if (!h) return fail(SNK_EINVAL, "handle is NULL");
+  h->reduce_enabled = on != 0;
+  if (h->rollout_cache) snk_graph_destroy(h->rollout_cache);
+  return SNK_OK;
+}
+
 extern "C" int snk_get_stats_global(snk_handle* h, double* h_stats, void* stream) {
   if (!h || !h_stats) return fail(SNK_EINVAL, "NULL argument");
+  if (h->peer.ranks > 0) {  // own running sums + the peers' latest pushes, as of now
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(snk_launch_sum_inbox(h->peer, h->p.stats, h->d_global, s));
+    CUDA_TRY(cudaMemcpyAsync(h_stats, h->d_global, sizeof(double) * SNK_NSTATS, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return SNK_OK;
+  }
   if (!h->comm) return snk_get_stats(h, h_stats, stream);  // one shard: the local sums are the global ones
   cudaStream_t s = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -990,7 +1110,7 @@ extern "C" int snk_comm_bench(snk_handle* h, int32_t iters, double* mean_us) {
 
 extern "C" int snk_comm_info(const snk_handle* h, int32_t* out /*[4]: ranks, rank, collectives issued (low 31 bits), nccl version*/) {
   if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
-  out[0] = h->comm ? h->comm_ranks : 1; out[1] = h->comm_rank; out[2] = (int32_t)(h->collectives & 0x7fffffff);
+  out[0] = (h->comm || h->peer.ranks > 0) ? h->comm_ranks : 1; out[1] = h->comm_rank; out[2] = (int32_t)(h->collectives & 0x7fffffff);
   int v = 0;
   if (g_nccl.so && g_nccl.GetVersion) g_nccl.GetVersion(&v);
   out[3] = v;

@@ -17,6 +17,8 @@ typedef uint32_t u32;
 typedef uint64_t u64;
 
 #define FULL 0xffffffffu
+#define SNK_MAX_PEERS 16        // ranks of one node that can share statistics through peer memory
+#define SNK_INBOX_STRIDE 64     // bytes per sender in an inbox: its SNK_NSTATS running sums
 
 // ---- private per-env record (u32 words); snakes start at word REC_SNAKE0, two words each:
 //      word A = head_slot | len << 16, word B = grow_to | vel << 16; classic fruits follow as u16.
@@ -28,6 +30,12 @@ typedef uint64_t u64;
 #define REC_SNAKE0 8
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_OBSERVE = 2 };
+
+// peer-memory form of the statistics reduction (snk_peer_connect): every rank's inbox as mapped into this process
+struct PeerArgs {
+  int ranks, rank;              // ranks == 0: off
+  u8* inbox[SNK_MAX_PEERS];     // cudaIpc mappings; [rank] is the local one
+};
 
 struct Params {
   int D, V, VV, S, F, K, C;     // C = 3K bytes per pixel
@@ -63,6 +71,7 @@ struct Params {
   double* stats;
   double* snap;                 // per-step copy of `stats` written by the last CTA of a step kernel (NULL: no per-step reduction)
   u32* ticket;                  // arrival counter behind `snap`
+  PeerArgs peer;                // peer-memory form: the first CTA of every step pushes the running sums to the peers
   u32* err;
   const u32* tape_vals;
   const u32* tape_bounds;

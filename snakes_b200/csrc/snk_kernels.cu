@@ -76,10 +76,28 @@ __device__ __forceinline__ void flush_stats(const Params& p, const WarpStats& st
   }
 }
 
-// End of every step kernel: the CTA's sums go to the handle's running statistics.  When the handle reduces its
-// statistics over the ranks every step (snk_comm_init: Params::snap set), the LAST CTA to arrive also copies the vector
-// into the snapshot slot of this step, which the side stream hands to ncclAllReduce while the next step runs
-// (monitor.py:57-78 aggregated over all shards).
+// The path's one inter-GPU exchange, fused into the step kernel and free of any rendezvous (snk_peer_connect).
+// Every statistic is a monotonic running sum, and an aligned 8-byte store is one transaction on NVLink, so the exchange
+// needs neither fences nor versions: at the START of step t + 1 eight threads of the first CTA read the rank's sums --
+// complete as of step t, the launch has just waited for the previous grid -- and store each into this rank's slot of
+// every peer's inbox (cudaIpc-mapped peer memory).  The stores are posted and drain while the CTA goes on to step its
+// envs: nothing waits for them, no collective kernel runs beside the step, no rank ever waits for another.  A reader sums
+// its own running sums and the eight-byte values the peers last pushed: the global statistics as of about one step ago
+// (monitor.py:57-78 aggregated over all shards), exact once every rank has pushed its final sums
+// (snk_get_stats_global does that push).
+__device__ __forceinline__ void peer_push(const Params& p, int tid) {
+  if (p.peer.ranks > 1 && blockIdx.x == 0 && tid < SNK_NSTATS && p.mode == MODE_STEP) {
+    const double v = __ldcg(&p.stats[tid]);
+    for (int g = 0; g < p.peer.ranks; ++g)
+      if (g != p.peer.rank) reinterpret_cast<volatile double*>(p.peer.inbox[g] + (size_t)p.peer.rank * SNK_INBOX_STRIDE)[tid] = v;
+  }
+}
+
+// End of every step kernel: the CTA's sums go to the handle's running statistics.  In the NCCL form of the per-step
+// reduction (snk_comm_init: Params::snap set) the LAST CTA to arrive also copies the vector into the snapshot slot of
+// this step, which a side stream hands to ncclAllReduce beside the next step.  (The peer-memory form pushes at the START
+// of the next step instead, peer_push: anything done here, at the very end of a launch, sits on the critical path --
+// a fenced push from the last CTA was measured at 7.5 us per step, because the next launch waits for this grid.)
 __device__ __forceinline__ void publish_stats(const Params& p, const double* s_stats, int tid) {
   __shared__ int s_last;
   __syncthreads();
@@ -163,6 +181,7 @@ __global__ void __launch_bounds__(BLOCK) k_step_tile(const Params p) {
   u32* sc = reinterpret_cast<u32*>(tmpl + tmpl_bytes) + warp * (p.RW + p.bm_words);
   u32* bm = sc + p.RW;
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  peer_push(p, tid);  // the running sums as of the previous step, to every peer (posted stores)
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.tmpl);
     uint4* dst = reinterpret_cast<uint4*>(tmpl);
@@ -276,6 +295,7 @@ __global__ void __launch_bounds__(128) k_lane_logic(const Params p) {
   __shared__ u32 s_bm[4][SPAWN_WORDS];  // per warp: scratch of group_spawn
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  peer_push(p, tid);  // the running sums as of the previous step, to every peer (posted stores)
   __syncthreads();
   LaneStats st = {0, 0, 0, 0, 0, 0, 0, 0};
   u32 errs = 0;
@@ -358,6 +378,7 @@ __global__ void __launch_bounds__(160, 5) k_step_lane_ws(const Params p) {
   const int PW = p.PW, LW = (blockDim.x >> 5) - PW;
   const int TE = p.TE, LPE = 32 / TE, E = p.E, IPB = 32 / TE;  // images per 32-env batch
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  peer_push(p, tid);  // the running sums as of the previous step, to every peer (posted stores)
   if (tid < 8) s_ready[tid] = 0;
   __syncthreads();
   const long long n_batches = (p.N + 31) / 32;
@@ -466,6 +487,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   // fetch) may overlap the tail of the previous launch in the stream; records, actions and every
   // output are only touched after the previous grid has completed and flushed.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  peer_push(p, tid);  // the running sums as of the previous step, to every peer (posted stores)
   if (b < n_batches && b * 32 + lane < p.N) raw = lane_fetch<S>(p, b * 32 + lane, stepping);
   bool have_image = false;
 #ifdef SNK_PHASE_TIMING  // experiment build (tools/phase.py): cycles per phase, summed over warps
@@ -554,6 +576,7 @@ __global__ void __launch_bounds__(256) k_step_dense(const Params p) {
   u32* sc = reinterpret_cast<u32*>(smem + ((VV + 15) & ~15));
   u32* bm = sc + p.RW;
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  peer_push(p, tid);  // the running sums as of the previous step, to every peer (posted stores)
   __syncthreads();
   WarpStats st = {0, 0, 0, 0, 0, 0, 0, 0};
   u32 errs = 0;
@@ -665,6 +688,7 @@ __global__ void __launch_bounds__(160, 5) k_step_rows(const Params p) {
   u32* sc = reinterpret_cast<u32*>(tiles + 2 * p.tile_stride);
   u32* bm = sc + p.RW;
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  peer_push(p, tid);  // the running sums as of the previous step, to every peer (posted stores)
   __syncthreads();
   WarpStats st = {0, 0, 0, 0, 0, 0, 0, 0};
   u32 errs = 0;
@@ -1102,17 +1126,32 @@ __global__ void k_extract_views(const u8* __restrict__ src, u8* __restrict__ dst
   const long long px0 = g * 4;
   if (px0 >= n_pixels) return;
   const int CO = 3 * n_out;
-  if (px0 + 4 <= n_pixels) {
+  if (px0 + 4 <= n_pixels && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
     u32 w[12];  // n_out <= 4
     u8* b = reinterpret_cast<u8*>(w);
     for (int q = 0; q < 4; ++q)
       for (int j = 0; j < CO; ++j) b[q * CO + j] = src[(px0 + q) * C + j];
     u32* d = reinterpret_cast<u32*>(dst + px0 * CO);
     for (int j = 0; j < CO; ++j) d[j] = w[j];
-  } else {
-    for (long long q = px0; q < n_pixels; ++q)
+  } else {  // the ragged tail, or a destination that is not word aligned (an odd slot of an odd-sized rollout buffer)
+    for (long long q = px0; q < n_pixels && q < px0 + 4; ++q)
       for (int j = 0; j < CO; ++j) dst[q * CO + j] = src[q * C + j];
   }
+}
+
+// snk_get_stats_global in the peer-memory form: push the rank's CURRENT sums to the peers (the final step's, which no
+// later step would push) and add up the own sums and what the peers have pushed so far
+__global__ void k_sum_inbox(const PeerArgs a, const double* __restrict__ stats, double* __restrict__ glob) {
+  const int k = threadIdx.x;
+  if (k >= SNK_NSTATS) return;
+  const double v = __ldcg(stats + k);
+  double sum = v;
+  for (int g = 0; g < a.ranks; ++g) {
+    if (g == a.rank) continue;
+    reinterpret_cast<volatile double*>(a.inbox[g] + (size_t)a.rank * SNK_INBOX_STRIDE)[k] = v;
+    sum += reinterpret_cast<const volatile double*>(a.inbox[a.rank] + (size_t)g * SNK_INBOX_STRIDE)[k];
+  }
+  glob[k] = sum;
 }
 
 __global__ void k_gen_actions(int8_t* actions, long long N, int S, long long env_id_base, u64 step, u64 seed, int n_actions) {
@@ -1275,6 +1314,13 @@ cudaError_t snk_launch_dump(const Params& p, u8* blob, const snk_state_layout& l
   k_dump<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, blob, lay, first, count);
   return cudaGetLastError();
 }
+
+cudaError_t snk_launch_sum_inbox(const PeerArgs& a, const double* stats, double* glob, cudaStream_t stream) {
+  k_sum_inbox<<<1, 32, 0, stream>>>(a, stats, glob);
+  return cudaGetLastError();
+}
+
+
 
 cudaError_t snk_launch_extract_views(const uint8_t* src, uint8_t* dst, long long n_pixels, int C, int n_out, cudaStream_t stream) {
   const long long n = (n_pixels + 3) / 4;

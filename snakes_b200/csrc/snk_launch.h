@@ -6,6 +6,7 @@
 #include "../../include/snk.h"
 
 struct Params;
+struct PeerArgs;
 enum { KIND_LANE = 0, KIND_TILE = 1, KIND_DENSE = 2, KIND_ROWS = 3 };
 
 struct LaunchPlan {
@@ -24,6 +25,7 @@ bool snk_lane_supported(int S, int K);
 cudaError_t snk_launch_step(const Params& p, int rules, const LaunchPlan& plan, cudaStream_t stream);
 cudaError_t snk_launch_upscale84(const uint8_t* native, uint8_t* out, long long N, int V, int C, int n_sm, cudaStream_t stream);
 cudaError_t snk_launch_dump(const Params& p, uint8_t* blob, const snk_state_layout& lay, long long first, long long count, cudaStream_t stream);
+cudaError_t snk_launch_sum_inbox(const PeerArgs& a, const double* stats, double* glob, cudaStream_t stream);
 cudaError_t snk_launch_extract_views(const uint8_t* src, uint8_t* dst, long long n_pixels, int C, int n_out, cudaStream_t stream);
 cudaError_t snk_launch_load(const Params& p, const uint8_t* blob, const snk_state_layout& lay, cudaStream_t stream);
 cudaError_t snk_launch_scripted_actions(const Params& p, int8_t* actions, uint64_t step, uint64_t seed, int eps_permille, cudaStream_t stream);

@@ -191,6 +191,24 @@ class Model(object):
             p.copy_(q)
 
 
+def _dist_world():
+    d = torch.distributed
+    return d.get_world_size() if d.is_available() and d.is_initialized() else 1
+
+
+def sync_model_across_ranks(model, src=0):
+    """Data-parallel learner: every rank builds its network from its own RNG, so the replicas must be made identical
+    before the first update (gradients are averaged afterwards, Model.train).  Broadcasts parameters from `src`."""
+    if _dist_world() > 1:
+        for prm in model.net.parameters():
+            torch.distributed.broadcast(prm.data, src)
+    return model
+
+
+def _is_rank0():
+    return _dist_world() == 1 or torch.distributed.get_rank() == 0
+
+
 def sf01(t):
     """swap and then flatten axes 0 and 1 (:222-227)."""
     return t.transpose(0, 1).reshape(t.shape[0] * t.shape[1], *t.shape[2:])
@@ -215,6 +233,8 @@ class Runner(object):
         self.mb_neglogp = torch.empty((nsteps, N), dtype=torch.float32, device=dev)
         self.mb_dones = torch.empty((nsteps, N), dtype=torch.bool, device=dev)
         self.full_actions = torch.zeros((N, env.S), dtype=torch.int8, device=dev)
+        self.main_spare = torch.empty((N, h, w, 3), dtype=torch.uint8, device=dev)  # main view after the rollout's last step
+        self.main_next = None
 
     def _views(self):
         """use_multi_agent_obs (:161-165): view 0 is the main snake's, view i + 1 opponent i's."""
@@ -230,18 +250,26 @@ class Runner(object):
         return a, v, nlp
 
     def run(self):
+        """The rollout loop of Runner.run (:178-198).  The env writes the main snake's view of the observation a step
+        returns straight into the slot the NEXT step's policy call reads it from (set_main_view_target: mb_obs[t + 1],
+        the last one into a spare slot), so mb_obs is filled by the env and the policy reads a contiguous [N,H,W,3]
+        tensor; the opponents' views stay in the env's own transient buffer."""
         env = self.env
         before = env.stats(False)
         for t in range(self.nsteps):
             views = self._views()
-            self.mb_obs[t].copy_(views[0])
-            a, v, nlp = self._act(views)
+            if t == 0:
+                self.mb_obs[0].copy_(self.main_next if self.main_next is not None else views[0])
+            a, v, nlp = self._act([self.mb_obs[t]] + views[1:])
             self.mb_actions[t], self.mb_values[t], self.mb_neglogp[t] = a, v, nlp
             self.mb_dones[t] = self.dones
+            env.set_main_view_target(self.mb_obs[t + 1] if t + 1 < self.nsteps else self.main_spare)
             self.obs, rew, dones, _ = env.step(self.full_actions)
             self.mb_rewards[t] = rew
             self.dones = dones.clone()
-        last_values = self.model.value(self.obs[..., 0:3])
+        env.set_main_view_target(None)
+        self.main_next = self.main_spare
+        last_values = self.model.value(self.main_spare)
         advs, returns = _rollout.gae(self.mb_rewards, self.mb_values, self.mb_dones, last_values, self.dones, self.gamma, self.lam)
         after = env.stats(False)
         # Monitor's episode records of this rollout in aggregate (every finished episode, not a sample)
@@ -307,13 +335,15 @@ def learn(env, nsteps=128, total_timesteps=int(1e6), ent_coef=0.01, lr=2.5e-4, v
     assert nbatch % nminibatches == 0
     nbatch_train = nbatch // nminibatches
     mk = lambda trainable: Model(ob_shape, n_act, ent_coef, vf_coef, max_grad_norm, arch, dev, trainable)
-    model = mk(True)
+    model = sync_model_across_ranks(mk(True))   # one model, N replicas: identical weights from the first update on
     opponent_models = [mk(False) for _ in range(S - 1)]
+    # opponent sampling uses `rng`, seeded identically on every rank, so all ranks load the same past selves
+    write = model_dir is not None and _is_rank0()   # checkpoints and opponent files are written by rank 0 only
     runner = Runner(env, model, opponent_models, nsteps, gamma, lam)
-    logger = KVLogger(csv_path, echo)
+    logger = KVLogger(csv_path if _is_rank0() else None, echo and _is_rank0())
     epbuf = deque()          # (episodes, return_sum, length_sum) per rollout, newest last; covers >= 100 episodes
     maxlen = 100
-    if model_dir:
+    if write:
         os.makedirs(model_dir, exist_ok=True)
     pool = [[] for _ in range(S - 1)]
     idx = [0] * (S - 1)
@@ -324,7 +354,7 @@ def learn(env, nsteps=128, total_timesteps=int(1e6), ent_coef=0.01, lr=2.5e-4, v
             pool[i][idx[i]] = snap
         else:
             pool[i].append(snap)
-        if model_dir:
+        if write:
             model.save(os.path.join(model_dir, "opponent%d_%d.pkl" % (i, idx[i])))
         idx[i] = (idx[i] + 1) % max_saved_opponents
 
@@ -368,9 +398,9 @@ def learn(env, nsteps=128, total_timesteps=int(1e6), ent_coef=0.01, lr=2.5e-4, v
             for name, val in zip(Model.loss_names, lossvals):
                 logger.logkv(name, val)
             logger.dumpkvs()
-        if save_interval and model_dir and (update % save_interval == 0 or update == 1):
+        if save_interval and write and (update % save_interval == 0 or update == 1):
             model.save(os.path.join(model_dir, "snake_model_num%d_%d.pkl" % (S, update)))
-    if model_dir:
+    if write:
         model.save(os.path.join(model_dir, "snake_model_num%d_final.pkl" % S))
     logger.close()
     return model, logger

@@ -104,6 +104,38 @@ class Infos(object):
         return [{"r": round(float(ret[i]), 6), "l": int(length[i]), "t": self._elapsed} for i in idx]
 
 
+class MonitorCSV(object):
+    """The per-episode log baselines' Monitor writes when it is given a file name (bench/monitor.py:27-36, :62-76):
+    a `#{"t_start": ..., "env_id": ...}` header line, then `r,l,t` rows, one per finished episode, in the order the
+    episodes ended.  (The reference's make_basic_env passes filename=None, utils.py:40, so it writes none; this is for
+    callers that want the file the plotting scripts read.)  Feed it the `infos` of every step."""
+
+    EXT = "monitor.csv"
+
+    def __init__(self, path, env_id="snake", t_start=None):
+        import json
+        import time
+        if not path.endswith(self.EXT):
+            path = path + "." + self.EXT if not path.endswith(".") else path + self.EXT
+        self.path = path
+        self.f = open(path, "wt")
+        self.f.write("#%s\n" % json.dumps({"t_start": time.time() if t_start is None else t_start, "env_id": env_id}))
+        self.f.write("r,l,t\n")
+        self.f.flush()
+        self.episodes = 0
+
+    def write(self, infos):
+        for ep in infos.episodes():
+            self.f.write("%s,%d,%s\n" % (ep["r"], ep["l"], ep["t"]))
+            self.episodes += 1
+        self.f.flush()
+
+    def close(self):
+        if self.f:
+            self.f.close()
+            self.f = None
+
+
 class StepGraph(object):
     """T env steps captured as one CUDA graph (snk_graph_create): a single launch per rollout,
     kernels linked by programmatic dependent-launch edges, no Python in the loop."""
@@ -377,6 +409,16 @@ class SnakeVecEnv(object):
             _lib.check(self._L.snk_set_obs_target(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel()))
         self._bind_buffers()
 
+    def set_main_view_target(self, tensor):
+        """Every following step / reset also writes the MAIN snake's view of all envs, packed [N,H,W,3], into `tensor`
+        (slot t of the learner's [nsteps,N,H,W,3] rollout buffer, ppo_multi_agent_new.py:181); None switches it off."""
+        if tensor is None:
+            _lib.check(self._L.snk_set_main_view_target(self._h, None, 0))
+        else:
+            assert tensor.is_cuda and tensor.dtype == torch.uint8 and tensor.is_contiguous()
+            _lib.check(self._L.snk_set_main_view_target(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel()))
+        self._main_target = tensor   # keep it alive
+
     def make_graph(self, actions, T=None, obs_out=None, rewards_out=None, dones_out=None, sync_back=False):
         """T steps as one CUDA graph launch (snk_graph_create).  actions: int8 CUDA tensor [B, N, S]; step t plays
         batch t % B (T defaults to B).  obs_out [T,N,H,W,3K] / rewards_out [T,N] f32 / dones_out [T,N] u8 redirect the
@@ -503,30 +545,63 @@ class SnakeVecEnv(object):
             all_reduce_stats(s)
         return dict(zip(_lib.STAT_NAMES, s.cpu().tolist()))
 
-    def init_comm(self, group=None):
-        """Sets up the path's one collective (snk_comm_init): from now on every step all-reduces the
-        8-double statistics vector over all ranks on a side stream (raw ncclAllReduce issued by the
-        C layer), read one step late through stats_global().  The NCCL id travels over the existing
-        torch.distributed group; without one (single process) this is a one-rank communicator."""
+    def init_comm(self, group=None, mode="p2p"):
+        """Sets up the path's one exchange: from now on every step sums the 8-double statistics vector over all ranks,
+        read about one step late through stats_global().
+        mode 'p2p' (default): fused into the step kernel -- its first CTA stores the rank's running sums (as of the
+        previous step) into every peer's inbox over NVLink (cudaIpc-mapped peer memory, posted 8-byte stores); no
+        collective kernel, no fence, no rendezvous (snk_peer_export / snk_peer_connect).  mode 'nccl': a raw ncclAllReduce per step issued by the C layer on a side
+        stream (snk_comm_init).  The handles / the NCCL id travel over the existing torch.distributed group; without
+        one (single process) both forms degenerate to one rank."""
         import torch.distributed as dist
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank(group) if world > 1 else 0
+        on_gpu = world > 1 and dist.get_backend(group) == "nccl"
+        if mode == "p2p":
+            mine = np.zeros(64, dtype=np.uint8)
+            _lib.check(self._L.snk_peer_export(self._h, mine.ctypes.data_as(C.c_void_p)))
+            handles = mine[None]
+            if world > 1:
+                t = torch.from_numpy(mine).to(self.device if on_gpu else "cpu")
+                out = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(out, t, group=group)
+                handles = np.ascontiguousarray(torch.stack(out).cpu().numpy())
+            torch.cuda.synchronize(self.device)
+            _lib.check(self._L.snk_peer_connect(self._h, handles.ctypes.data_as(C.c_void_p), world, rank))
+            if world > 1:
+                dist.barrier(group=group)   # every rank has mapped every inbox before anybody pushes
+            self.comm_mode = "p2p"
+            return world
+        if mode != "nccl":
+            raise ValueError("mode must be 'p2p' or 'nccl'")
         ident = np.zeros(128, dtype=np.uint8)
         if rank == 0:
             _lib.check(self._L.snk_comm_unique_id(ident.ctypes.data_as(C.c_void_p)))
         if world > 1:
-            on_gpu = dist.get_backend(group) == "nccl"
             t = torch.from_numpy(ident).to(self.device if on_gpu else "cpu")
             dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             ident = np.ascontiguousarray(t.cpu().numpy())
         torch.cuda.synchronize(self.device)
         _lib.check(self._L.snk_comm_init(self._h, ident.ctypes.data_as(C.c_void_p), world, rank))
+        self.comm_mode = "nccl"
         return world
 
+    def comm_enable(self, on=True):
+        """A/B switch of the per-step reduction (graphs made afterwards follow it)."""
+        _lib.check(self._L.snk_comm_enable(self._h, 1 if on else 0))
+
     def stats_global(self):
-        """Statistics summed over all ranks as of the last completed per-step reduction (after init_comm)."""
+        """Statistics summed over all ranks (after init_comm).  NCCL form: as of the last completed per-step all-reduce.
+        Peer form: this rank's sums plus what the peers last pushed -- about one step old while the ranks are stepping;
+        called by all ranks after their last step it is exact (it pushes the final sums, waits at a barrier of the
+        torch.distributed group, then adds up)."""
         out = np.zeros(_lib.NSTATS, dtype=np.float64)
         _lib.check(self._L.snk_get_stats_global(self._h, out.ctypes.data_as(C.c_void_p), self._stream()))
+        if getattr(self, "comm_mode", None) == "p2p":
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.barrier()   # every rank's final push has been issued and completed (the call above synchronised)
+                _lib.check(self._L.snk_get_stats_global(self._h, out.ctypes.data_as(C.c_void_p), self._stream()))
         return dict(zip(_lib.STAT_NAMES, out.tolist()))
 
     def comm_latency_us(self, iters=200):

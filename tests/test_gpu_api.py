@@ -191,15 +191,17 @@ def test_dump_state_range_equals_slice(sb):
         env.close()
 
 
-def test_single_rank_comm_and_graph(sb):
-    """snk_comm_init with one rank: the per-step all-reduce runs (side stream, one per step, also inside a CUDA graph)
-    and stats_global() equals the local sums once the stream has drained."""
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_single_rank_comm_and_graph(sb, mode):
+    """The per-step statistics reduction with one rank, in both forms (peer-memory pushes fused into the step kernel;
+    ncclAllReduce on a side stream): it runs once per step, also inside a CUDA graph, changes no result, and
+    stats_global() equals the local sums.  (Two ranks: tests/test_gpu_multirank.py.)"""
     import torch
     N, T = 2048, 24
     env = sb.SnakeVecEnv(N, size=10, n_snakes=2, seed=2)
     ref = sb.SnakeVecEnv(N, size=10, n_snakes=2, seed=2)
     env.reset(); ref.reset()
-    assert env.init_comm() == 1
+    assert env.init_comm(mode=mode) == 1
     acts = torch.stack([ref.gen_actions(t, 5).clone() for t in range(T)])
     for t in range(5):
         env.step(acts[t]); ref.step(acts[t])
@@ -215,6 +217,51 @@ def test_single_rank_comm_and_graph(sb):
     env.step(acts[0]); ref.step(acts[0])
     assert env.stats_global() == ref.stats(reduce=False) and torch.equal(env.obs, ref.obs)
     g.close(); env.close(); ref.close()
+
+
+def test_main_view_target(sb):
+    """snk_set_main_view_target: view 0 of every step, packed [N,H,W,3], lands in the caller's slot while all K views
+    stay in the env's own buffer (f1: the learner's rollout keeps the main view only, ppo_multi_agent_new.py:181)."""
+    import torch
+    for kw in (dict(size=19, n_snakes=2), dict(size=10, n_snakes=3, rules="cut"), dict(size=19, n_snakes=2, obs_mode="atari84")):
+        N = 203
+        env = sb.SnakeVecEnv(N, seed=5, **kw)
+        H = env.obs.shape[1]
+        slots = torch.zeros((5, N, H, H, 3), dtype=torch.uint8, device=env.device)
+        env.set_main_view_target(slots[0])
+        obs = env.reset()
+        assert torch.equal(slots[0], obs[..., 0:3])
+        for t in range(1, 5):
+            env.set_main_view_target(slots[t])
+            obs, _, _, _ = env.step(env.gen_actions(t, 2))
+            assert torch.equal(slots[t], obs[..., 0:3]), t
+            assert obs.shape[-1] == 3 * env.K
+        env.set_main_view_target(None)
+        keep = slots[4].clone()
+        env.step(env.gen_actions(9, 2))
+        assert torch.equal(slots[4], keep)
+        env.close()
+
+
+def test_monitor_csv(sb, tmp_path):
+    """MonitorCSV writes the file baselines' Monitor writes (bench/monitor.py): json header, r,l,t rows per episode."""
+    import csv
+    import json
+    env = sb.SnakeVecEnv(64, size=10, n_snakes=2, seed=1)
+    env.reset()
+    mon = sb.MonitorCSV(str(tmp_path / "0"), env_id="snake-multiple-test-v0")
+    total = 0
+    for t in range(40):
+        _, _, dones, infos = env.step(env.gen_actions(t, 3))
+        mon.write(infos)
+        total += int(dones.sum())
+    mon.close()
+    lines = open(mon.path).read().splitlines()
+    assert mon.path.endswith("0.monitor.csv") and lines[0].startswith("#") and json.loads(lines[0][1:])["env_id"] == "snake-multiple-test-v0"
+    rows = list(csv.DictReader(lines[1:]))
+    assert len(rows) == total == mon.episodes and total > 20
+    assert all(int(r["l"]) >= 1 and float(r["r"]) >= -1.0 and float(r["t"]) >= 0 for r in rows)
+    env.close()
 
 
 def test_obs_target_rollout_slot(sb):

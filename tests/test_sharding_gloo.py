@@ -74,3 +74,47 @@ def test_two_rank_sharding_matches_single_process():
         assert np.array_equal(rew, rewards[base:base + count])
         covered += count
     assert covered == TOTAL
+
+
+def _learner_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from snakes_b200 import selfplay
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                       # every rank initialises ITS network differently ...
+    model = selfplay.Model((12, 12, 3), 5, device="cpu")
+    before = torch.cat([p.detach().flatten() for p in model.net.parameters()]).clone()
+    selfplay.sync_model_across_ranks(model)             # ... and must start from rank 0's weights
+    g = torch.Generator().manual_seed(7 + rank)         # different data per rank (sharded envs)
+    for _ in range(3):
+        n = 64
+        obs = torch.randint(0, 256, (n, 12, 12, 3), dtype=torch.uint8, generator=g)
+        ret, val, nlp = torch.randn(n, generator=g), torch.randn(n, generator=g), torch.rand(n, generator=g) + 1.0
+        act = torch.randint(0, 5, (n,), generator=g)
+        model.train(2.5e-4, 0.2, obs, ret, None, act, val, nlp)
+    after = torch.cat([p.detach().flatten() for p in model.net.parameters()])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (before.numpy(), after.numpy()))
+    if rank == 0:
+        out.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_learner_replicas_stay_identical():
+    """the data-parallel learner averaged gradients but never synchronised the initial weights.  Two
+    ranks with different seeds and different data: after sync_model_across_ranks + 3 updates the replicas are equal."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_learner_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (b0, a0), (b1, a1) = gathered
+    assert not np.array_equal(b0, b1)          # they did start different
+    assert np.array_equal(a0, a1)              # and ended identical, bit for bit
+    assert not np.array_equal(a0, b0)          # after real updates
