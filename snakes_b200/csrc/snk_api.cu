@@ -64,6 +64,13 @@ struct snk_handle {
   LaunchPlan plan;
   int n_sm;
   uint8_t* d_obs_own;     // native observations (the step kernels' output)
+  // regime-adaptive lane path: `plan` is the fused kernel, `plan_alt` the two-kernel form (k_lane_logic + k_lane_paint2)
+  LaunchPlan plan_alt;
+  bool have_alt, use_alt;
+  int restore_thr_alt;
+  double* h_regime;            // mapped pinned host memory [2]: env-steps, body cells (Params::regime_out)
+  double reg_steps0, reg_cells0, alt_hi, alt_lo;
+  const uint8_t* obs_current;  // where the native observations of the CURRENT state are (NULL: not encoded since the state changed)
   uint8_t* d_obs84_own;   // obs_mode atari84: the 84x84 images handed to the caller
   uint8_t* d_obs_user;    // what snk_get_buffers reports: own buffer or the caller's target
   uint8_t* d_main_target; // snk_set_main_view_target: view 0 of every step, packed [N][H][W][3] (NULL = off)
@@ -235,6 +242,7 @@ struct snk_graph {
   // arguments it was captured with (snk_rollout's cache key)
   const int8_t* d_actions; int32_t n_batches; uint8_t* d_obs; float* d_reward; uint8_t* d_done; uint32_t flags;
   uint8_t* obs_target; bool with_comm, with_push;
+  const uint8_t* last_native_obs;  // where the graph's last step leaves the native observations
   double* d_slots;  // with a communicator: [T] snapshot slots + [T] all-reduced slots, one pair per step (no reuse inside a launch)
 };
 
@@ -293,6 +301,7 @@ extern "C" int snk_create_ex(const snk_config* cfg, const char* debug_opts, snk_
   if (h->cfg.max_steps == 0) h->cfg.max_steps = 2000;
   h->launches = 0;
   h->d_main_target = nullptr;
+  h->obs_current = nullptr; h->have_alt = false; h->use_alt = false; h->h_regime = nullptr; h->reg_steps0 = h->reg_cells0 = 0.0;
   h->d_obs_own = nullptr; h->d_actions_own = nullptr; h->d_blob = nullptr; h->blob_bytes = 0; h->d_views = nullptr; h->views_bytes = 0;
   h->d_tape_vals = h->d_tape_bounds = nullptr; h->d_tape_off = nullptr;
   h->comm = nullptr; h->comm_ranks = 1; h->comm_rank = 0; h->side = nullptr; h->cap_stream = nullptr;
@@ -381,28 +390,33 @@ extern "C" int snk_create_ex(const snk_config* cfg, const char* debug_opts, snk_
     plan.ws = plan.kind == KIND_LANE && (have_lv ? lv == "ws" : (small_image && S == 1));
     plan.split = plan.kind == KIND_LANE && (have_lv ? lv == "split" : (small_image && S > 1));
     plan.pdl = dbg_int(dbg, "pdl", 1) != 0;
+    plan.paint2 = plan.split && dbg_int(dbg, "paint2", 1) != 0;
     p.PW = 2;
     logic_warps = dbg_int(dbg, "logic_warps", 3);
     if (logic_warps < 1 || logic_warps > 3) logic_warps = 3;
   }
   p.CW = (p.cap - 1 + 15) / 16;
+  // lane path geometry: te envs per warp image, epw envs stepped per warp batch (a multiple of te)
+  auto lane_geometry = [&](int te, int epw) {
+    p.TE = te; p.EPW = epw;
+    p.tile_stride = (int)(((size_t)te * p.E + 127) & ~(size_t)127);
+    // un-paint by zero-fill + border redraw (lane_restore) once a lane would walk more than restore_thr segments:
+    // the restore costs one 16-byte store per 512 bytes of image plus the border units of one env spread over its
+    // LPE lanes; a walked segment costs about 16 instructions.  Measured on B200 (2x19x19, 131072 envs, fruit-seeking
+    // policy, sum of lengths 22): thresholds 3 / 5 / 8 / 12 -> 145.9 / 145.1 / 146.8 / 152.9 us, always-walk 161.1 us;
+    // random actions (sum of lengths 4.4) unchanged.  restore_thr overrides (0 = always walk).
+    const int U = (p.C & 1) ? 1 : 2, LPE = 32 / te;
+    const int border_units = (2 * (V * p.C + p.C) + (V - 3) * 2 * p.C) / U;
+    const int stores = (int)((size_t)te * p.E / 512) + border_units / LPE;
+    p.restore_thr = dbg_int(dbg, "restore_thr", stores / 16 < 3 ? 3 : stores / 16);
+    plan.smem = (size_t)(plan.paint2 ? 1 : 2) * p.tile_stride + (size_t)dbg_int(dbg, "extra_smem", 0);  // extra_smem: fewer resident image buffers per SM (experiment)
+    p.n_groups = (N + epw - 1) / epw;
+  };
   if (plan.kind == KIND_LANE) {
     p.RW = (REC_SNAKE0 + 2 * S + 2 + 3) & ~3;
-    p.TE = TE; p.W = 32;
-    p.tile_stride = (int)(((size_t)TE * p.E + 127) & ~(size_t)127);
-    {  // un-paint by zero-fill + border redraw (lane_restore) once a lane would walk more than restore_thr segments:
-       // the restore costs one 16-byte store per 512 bytes of image plus the border units of one env spread over its
-       // LPE lanes; a walked segment costs about 16 instructions.  Measured on B200 (2x19x19, 131072 envs, fruit-seeking
-       // policy, sum of lengths 22): thresholds 3 / 5 / 8 / 12 -> 145.9 / 145.1 / 146.8 / 152.9 us, always-walk 161.1 us;
-       // random actions (sum of lengths 4.4) unchanged.  restore_thr overrides (0 = always walk).
-      const int U = (p.C & 1) ? 1 : 2, LPE = 32 / TE;
-      const int border_units = (2 * (V * p.C + p.C) + (V - 3) * 2 * p.C) / U;
-      const int stores = (int)((size_t)TE * p.E / 512) + border_units / LPE;
-      p.restore_thr = dbg_int(dbg, "restore_thr", stores / 16 < 3 ? 3 : stores / 16);
-    }
+    p.W = 32;
     plan.block = plan.ws ? 32 * (p.PW + logic_warps) : 64;
-    plan.smem = (size_t)2 * p.tile_stride + (size_t)dbg_int(dbg, "extra_smem", 0);  // extra_smem: fewer resident image buffers per SM (experiment)
-    p.n_groups = (N + 31) / 32;
+    lane_geometry(TE, 32);
   } else if (plan.kind == KIND_TILE) {
     p.W = W; plan.block = 32 * W; plan.smem = smem_tile;
     p.n_groups = (N + W - 1) / W;
@@ -417,12 +431,74 @@ extern "C" int snk_create_ex(const snk_config* cfg, const char* debug_opts, snk_
     if (plan.smem > 200 * 1024) { snk_destroy(h); return fail(SNK_EINVAL, "board too large for shared memory"); }
   }
   CUDA_TRY_H(snk_plan(cfg->rules, plan, h->n_sm, S, K));
+  if (plan.kind == KIND_LANE && !plan.ws && !plan.split) {
+    // Small shards.  A warp's pass (logic of its batch, then one image after the other) is a serial chain, and a lane
+    // per env keeps 32 envs on it; when the shard has fewer 32-env batches than the GPU holds warps (4 096 envs of
+    // 2x10x10 = 128 warps on 148 SMs: 14 us per step, all of it one warp's latency) the batch shrinks to 16 / 8 / 4 envs
+    // -- the idle lanes cost issue slots nobody wants, the chain gets shorter (one image, painted by 32/epw lanes per
+    // env) -- as long as every batch still finds a resident warp.  epw=<n> overrides.
+    const int forced = dbg_int(dbg, "epw", 0);
+    int te = TE, epw = 32;
+    for (int cand = 16; cand >= 4; cand >>= 1) {
+      if (cand % p.G != 0 || (forced && cand < forced)) break;
+      lane_geometry(cand < TE ? cand : TE, cand);
+      CUDA_TRY_H(snk_plan(cfg->rules, plan, h->n_sm, S, K));
+      if (!forced && (N + cand - 1) / cand > (long long)plan.max_grid * 2) break;  // more batches than resident warps (2 per CTA)
+      te = p.TE; epw = cand;
+    }
+    lane_geometry(te, epw);
+    CUDA_TRY_H(snk_plan(cfg->rules, plan, h->n_sm, S, K));
+  }
   {
     long long work = plan.kind == KIND_LANE ? (p.n_groups + 1) / 2 : p.n_groups;  // lane: 2 warps per CTA
-    if (plan.split) work = ((N + p.TE - 1) / p.TE + 1) / 2;                       // paint kernel: one image per warp
+    if (plan.split) work = plan.paint2 ? (N + p.TE - 1) / p.TE : ((N + p.TE - 1) / p.TE + 1) / 2;  // paint kernels: one image per CTA / per warp
     if (plan.ws) { const int LW = plan.block / 32 - p.PW; work = (p.n_groups + LW - 1) / LW; }
     plan.grid = (int)(work < plan.max_grid ? work : plan.max_grid);
     if (plan.grid < 1) plan.grid = 1;
+  }
+  // Regime-adaptive lane path.  With short bodies the fused kernel wins (2x19x19, 131 072 envs, random actions: 64.5 us
+  // against 73.3 us for the two-kernel form: the logic hides under the observation stream); with long bodies its warps
+  // -- ten per SM, each a serial chain through 78 KB of code, 2.4x the instruction cache -- fall behind and the two
+  // small kernels win.  Measured on one box, mean body cells per env 5.8 / 8.6 / 12.8 / 22.2 (fruit-seeking policy with
+  // 70 / 40 / 20 / 5 % random actions): fused 72.6 / 83.0 / 92.4 / 109.9 us, two kernels 75.9 / 79.8 / 85.6 / 93.4 us.  The host cannot know
+  // the regime without the statistics, so the first CTA of every step posts the running sums into mapped host memory
+  // (peer_push) and regime_update() below reads them -- no synchronisation, a step or two late, which is early enough
+  // for a quantity that moves over hundreds of steps.  Results are bit-identical either way.  adaptive=0 turns it off.
+  {
+    std::string lv;
+    const bool eligible = plan.kind == KIND_LANE && !plan.ws && !plan.split && p.EPW == 32 && !dbg_get(dbg, "lane", &lv) &&
+                          dbg_int(dbg, "adaptive", 1) != 0;
+    if (eligible) {
+      h->plan_alt = plan;
+      LaunchPlan& alt = h->plan_alt;
+      alt.split = true; alt.paint2 = true; alt.block = 64;
+      alt.smem = (size_t)p.tile_stride;
+      if (snk_plan(cfg->rules, alt, h->n_sm, S, K) == cudaSuccess) {
+        const long long work = (N + p.TE - 1) / p.TE;
+        alt.grid = (int)(work < alt.max_grid ? work : alt.max_grid);
+        if (alt.grid < 1) alt.grid = 1;
+        const int U = (p.C & 1) ? 1 : 2, LPE = 64 / p.TE;
+        const int border_units = (2 * (V * p.C + p.C) + (V - 3) * 2 * p.C) / U;
+        const int stores = (int)((size_t)p.TE * p.E / 1024) + border_units / LPE;
+        h->restore_thr_alt = dbg_int(dbg, "restore_thr", stores / 16 < 3 ? 3 : stores / 16);
+        // thresholds in body cells per env, hysteresis between them; measured at 2646 bytes of image per env and scaled
+        // with the image (the larger the image, the longer the stream hides the fused kernel's logic)
+        const int hi = dbg_int(dbg, "alt_hi", 0);
+        h->alt_hi = hi > 0 ? (double)hi : 8.0 * (double)p.E / 2646.0;
+        h->alt_lo = 0.75 * h->alt_hi;
+        void* hp = nullptr;
+        if (cudaHostAlloc(&hp, 2 * sizeof(double), cudaHostAllocMapped) == cudaSuccess) {
+          void* dp = nullptr;
+          if (cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+            h->h_regime = (double*)hp; h->h_regime[0] = h->h_regime[1] = 0.0;
+            h->host_allocs.push_back(std::make_pair(hp, 2 * sizeof(double)));
+            p.regime_out = (double*)dp;
+            h->have_alt = true;
+          } else cudaFreeHost(hp);
+        }
+        cudaGetLastError();
+      }
+    }
   }
 
   // device buffers
@@ -526,6 +602,19 @@ struct CaptureCtx {  // a step being recorded into a CUDA graph
   int T;
 };
 
+// Fused or two-kernel form for the next launch (see snk_create_ex): mean body cells per env over the steps since the last
+// decision, from the sums the step kernels post into mapped host memory.
+static void regime_update(snk_handle* h) {
+  if (!h->have_alt) return;
+  const double steps = ((volatile double*)h->h_regime)[0], cells = ((volatile double*)h->h_regime)[1];
+  if (steps < h->reg_steps0 || cells < h->reg_cells0) { h->reg_steps0 = steps; h->reg_cells0 = cells; return; }  // statistics were reset
+  if (steps - h->reg_steps0 < (double)h->p.N) return;  // less than one whole step of news
+  const double mean = (cells - h->reg_cells0) / (steps - h->reg_steps0);
+  h->reg_steps0 = steps; h->reg_cells0 = cells;
+  if (mean > h->alt_hi) h->use_alt = true;
+  else if (mean < h->alt_lo) h->use_alt = false;
+}
+
 static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_t* d_mask, cudaStream_t stream,
                   const RolloutSlot* slot = nullptr, const CaptureCtx* cap = nullptr) {
   const bool capturing = cap != nullptr;
@@ -564,8 +653,13 @@ static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_
     }
   }
   p.snap = snap;
-  CUDA_TRY(snk_launch_step(p, h->cfg.rules, h->plan, stream));
-  h->launches += (h->plan.split && mode != MODE_OBSERVE) ? 2 : 1;
+  if (mode == MODE_STEP) regime_update(h);
+  const bool alt = h->have_alt && h->use_alt;
+  const LaunchPlan& plan = alt ? h->plan_alt : h->plan;
+  if (alt) p.restore_thr = h->restore_thr_alt;
+  CUDA_TRY(snk_launch_step(p, h->cfg.rules, plan, stream));
+  if (!capturing) h->obs_current = p.obs;
+  h->launches += (plan.split && mode != MODE_OBSERVE) ? 2 : 1;
   if (reduce) {
     // side stream: all-reduce this step's snapshot while the next step runs; its result is read one step late
     cudaEvent_t es = capturing ? h->cev_step[0] : h->ev_step[sl], er = capturing ? h->cev_red[0] : h->ev_red[sl];
@@ -642,12 +736,16 @@ static int graph_create_impl(snk_handle* h, const int8_t* d_actions, int32_t n_b
     slot.reward = d_reward ? d_reward + (size_t)t * p.N : nullptr;
     slot.done = d_done ? d_done + (size_t)t * p.N : nullptr;
     if (scripted) {  // the policy kernel reads the state step t-1 left and writes this step's actions
-      if (snk_launch_scripted_actions(h->p, h->d_actions_own, scripted->step0 + (uint64_t)t, scripted->seed, scripted->eps_permille, s) != cudaSuccess)
+      // (occupancy from the previous captured step's observations; step 0 walks the bodies: the graph cannot know where
+      // the observations of the state it will be launched on are)
+      if (snk_launch_scripted_actions(h->p, h->d_actions_own, scripted->step0 + (uint64_t)t, scripted->seed, scripted->eps_permille,
+                                      t ? g->last_native_obs : nullptr, s) != cudaSuccess)
         rc = fail(SNK_ECUDA, "capture: scripted policy kernel");
       h->launches++;
     }
     const CaptureCtx cap = {t, g->d_slots, T};
     if (rc == SNK_OK) rc = launch(h, MODE_STEP, d_actions + (size_t)(t % n_batches) * p.N * p.S, nullptr, s, &slot, &cap);
+    g->last_native_obs = (slot.obs && h->cfg.obs_mode != SNK_OBS_ATARI84) ? slot.obs : h->p.obs;
   }
   if (rc == SNK_OK && reducing) {  // join the side branch (its last all-reduce) back into the origin stream
     if (cudaStreamWaitEvent(s, h->cev_red[0], 0) != cudaSuccess) rc = fail(SNK_ECUDA, "cudaStreamWaitEvent (capture join)");
@@ -696,6 +794,7 @@ extern "C" int snk_graph_launch(snk_graph* g, void* stream) {
     if (rc) return rc;
   }
   CUDA_TRY(cudaGraphLaunch(g->exec, s));
+  h->obs_current = g->last_native_obs;
   h->launches += g->launches_per_run;
   h->collectives += g->collectives_per_run;
   if (g->with_comm) {
@@ -918,6 +1017,7 @@ extern "C" int snk_load_state(snk_handle* h, const void* h_src, size_t bytes) {
   if (rc) return rc;
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(h->d_blob, h_src, h->lay.total_bytes, cudaMemcpyHostToDevice));
+  h->obs_current = nullptr;
   CUDA_TRY(snk_launch_load(h->p, h->d_blob, h->lay, 0));
   h->launches++;
   CUDA_TRY(cudaDeviceSynchronize());
@@ -1130,7 +1230,7 @@ extern "C" int snk_gen_scripted_actions(snk_handle* h, int8_t* d_actions, uint64
   if (h->p.family != 1 || h->cfg.rules != SNK_RULES_CLASSIC)
     return fail(SNK_EINVAL, "the scripted policy needs a lane-family configuration with classic rules");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  CUDA_TRY(snk_launch_scripted_actions(h->p, d_actions, step, seed, eps_permille, (cudaStream_t)stream));
+  CUDA_TRY(snk_launch_scripted_actions(h->p, d_actions, step, seed, eps_permille, h->obs_current, (cudaStream_t)stream));
   h->launches++;
   return SNK_OK;
 }
@@ -1164,7 +1264,8 @@ extern "C" int snk_launch_count(const snk_handle* h, uint64_t* out) {
 
 extern "C" int snk_launch_info(const snk_handle* h, int32_t* out /*[6]: kind, grid, block, smem, occupancy, envs per CTA*/) {
   if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
-  out[0] = h->plan.kind; out[1] = h->plan.grid; out[2] = h->plan.block; out[3] = (int32_t)h->plan.smem;
-  out[4] = h->plan.occupancy; out[5] = h->plan.kind == KIND_LANE ? 64 : h->p.W;
+  const LaunchPlan& pl = (h->have_alt && h->use_alt) ? h->plan_alt : h->plan;
+  out[0] = pl.kind; out[1] = pl.grid; out[2] = pl.block; out[3] = (int32_t)pl.smem;
+  out[4] = pl.occupancy; out[5] = pl.kind == KIND_LANE ? (pl.split ? (pl.paint2 ? h->p.TE : 2 * h->p.TE) : pl.ws ? 32 * (pl.block / 32 - h->p.PW) : 2 * h->p.EPW) : h->p.W;
   return SNK_OK;
 }

@@ -45,6 +45,7 @@ struct Params {
   int GBW;                      // lane family: words of the per-env fruit bitmap (adversarial / cut)
   int family, CW;               // 0 = ring bodies (tile / dense kernels), 1 = chain-coded bodies (lane kernel); chain words per snake
   int TE, tile_stride;          // lane kernel: envs per warp image, bytes between warp images
+  int EPW;                      // fused lane kernel: envs stepped per warp batch (32; 16/8/4 when the shard is too small to give every resident warp a batch)
   int store_mode;               // lane kernel image store: 0 = TMA bulk copy, 1 = LDS.128 + STG.128 by the warp
   int obs_evict_first, rec_evict_last;  // L2 policies: observation stream evict-first, env records evict-last
   int R;                        // rows kernel: image rows per chunk buffer
@@ -71,6 +72,7 @@ struct Params {
   double* stats;
   double* snap;                 // per-step copy of `stats` written by the last CTA of a step kernel (NULL: no per-step reduction)
   u32* ticket;                  // arrival counter behind `snap`
+  double* regime_out;           // mapped host memory [2]: running env-steps / body cells, posted by the first CTA of every step (NULL: off)
   PeerArgs peer;                // peer-memory form: the first CTA of every step pushes the running sums to the peers
   u32* err;
   const u32* tape_vals;

@@ -86,6 +86,11 @@ __device__ __forceinline__ void flush_stats(const Params& p, const WarpStats& st
 // (monitor.py:57-78 aggregated over all shards), exact once every rank has pushed its final sums
 // (snk_get_stats_global does that push).
 __device__ __forceinline__ void peer_push(const Params& p, int tid) {
+  // the same moment serves the host's choice between the fused and the two-kernel form of the lane path (snk_api.cu,
+  // regime_update): running env-steps and body cells as of the previous step, two posted 8-byte stores into mapped host
+  // memory, read there without any synchronisation
+  if (p.regime_out && blockIdx.x == 0 && tid < 2 && p.mode == MODE_STEP)
+    reinterpret_cast<volatile double*>(p.regime_out)[tid] = __ldcg(&p.stats[tid ? SNK_STAT_BODY_CELLS : SNK_STAT_ENV_STEPS]);
   if (p.peer.ranks > 1 && blockIdx.x == 0 && tid < SNK_NSTATS && p.mode == MODE_STEP) {
     const double v = __ldcg(&p.stats[tid]);
     for (int g = 0; g < p.peer.ranks; ++g)
@@ -289,12 +294,16 @@ __device__ __forceinline__ void reduce_lane_stats(const Params& p, LaneStats st,
 // ---- split form of the lane path: game logic at full occupancy, then the observation writer.
 // k_lane_logic: one THREAD per env, no shared-memory image, so many warps per SM hide the HBM
 // latency of the record / chain / action loads.
+// 7 CTAs per SM (72 registers) for one or two snakes: 131 072 envs are 1 024 CTAs, one wave on 148 x 7 slots where the
+// compiler's own 92 registers (5 CTAs per SM) made it two (long bodies: 96.7 -> 92.1 us per step); three and four snakes
+// would spill (120-320 bytes) and stay as they are
 template <int S, int RULES>
-__global__ void __launch_bounds__(128) k_lane_logic(const Params p) {
+__global__ void __launch_bounds__(128, (S <= 2 ? 7 : 1)) k_lane_logic(const Params p) {
   __shared__ double s_stats[SNK_NSTATS];
   __shared__ u32 s_bm[4][SPAWN_WORDS];  // per warp: scratch of group_spawn
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous step's observation writer still reads the records
   peer_push(p, tid);  // the running sums as of the previous step, to every peer (posted stores)
   __syncthreads();
   LaneStats st = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -320,6 +329,7 @@ __global__ void __launch_bounds__(128) k_lane_logic(const Params p) {
     }
     if (valid) lane_store<S>(p, e, env);
   }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the observation writer may start its prologue
   reduce_lane_stats(p, st, errs, s_stats, lane);
   publish_stats(p, s_stats, tid);
 }
@@ -359,6 +369,156 @@ __global__ void __launch_bounds__(64) k_lane_paint(const Params p) {
     item = next;
   }
   if (lane == 0) bulk_wait_all();
+}
+
+
+// k_lane_paint2: the observation writer with TWO warps per image buffer.  The image buffers are what an SM runs out
+// of (10 at 2x19x19), so with one warp each the SM holds 10 warps and every one of them is a serial chain paint ->
+// bulk store -> wait -> un-paint; here the 64 threads of a CTA share one buffer (LPE = 64/TE lanes per env), which
+// halves the trips of every per-env loop (an image takes as long as its longest snake), halves the zero-fill of the
+// restore, and doubles the warps that cover each other's latencies.  CTA-wide barriers take the place of __syncwarp.
+// Launched programmatically behind k_lane_logic: the border image is fetched before griddepcontrol.wait.
+template <int K>
+__device__ __forceinline__ void cta_restore(u8* tile, int n16, u8* img, int V, int sub, int LPE, int tid, int NT) {
+  constexpr int C = 3 * K, U = (C & 1) ? 1 : 2, PU = 2 * C / U;
+  uint4* t4 = reinterpret_cast<uint4*>(tile);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < n16; i += NT) t4[i] = z;
+  __syncthreads();
+  const int RB = V * C;
+  const int n_edge = (RB + C) / U;
+  u8* bot = img + RB * (V - 1) - C;
+  for (int j = sub; j < n_edge; j += LPE) {
+    if (U == 2) { *reinterpret_cast<u16*>(img + 2 * j) = 0xffffu; *reinterpret_cast<u16*>(bot + 2 * j) = 0xffffu; }
+    else { img[j] = 0xff; bot[j] = 0xff; }
+  }
+  for (int x = 1 + sub; x <= V - 3; x += LPE) {
+    u8* q = img + x * RB + RB - C;
+#pragma unroll
+    for (int r = 0; r < PU; ++r) {
+      if (U == 2) *reinterpret_cast<u16*>(q + 2 * r) = 0xffffu; else q[r] = 0xff;
+    }
+  }
+}
+
+// fruits, then the snakes in index order (get_ob_for_snake :35-58); `paint` false = the same walk writes zeros
+template <int S, int RULES, int K>
+__device__ __forceinline__ void cta_paint(const Params& p, const PaintEnv<S>& pe, long long e_owner, int sub, int LPE, u8* img, bool paint) {
+  constexpr int C = 3 * K;
+  const int V = p.V, F = p.F, sh = 31 - __clz(LPE);
+  const u8 red = paint ? 255 : 0;
+  if (RULES == SNK_RULES_CLASSIC) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      if (pe.valid && f < F && (f & (LPE - 1)) == sub) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) img[pe.fruit[f] * C + 3 * k] = red;
+      }
+    }
+  } else if (pe.valid) {
+    const u32* gb = p.gbits + e_owner * p.GBW;
+    for (int w = sub; w < p.GBW; w += LPE) {
+      for (u32 bits = gb[w]; bits; bits &= bits - 1) {
+        const int pid = 32 * w + __ffs(bits) - 1;
+        if (!(__ldg(p.cellinfo + pid) >> 31)) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) img[pid * C + 3 * k] = red;
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    if (pe.valid) {
+      // lane `sub` takes the contiguous run [sub * r, sub * r + r) of the snake's segments: one popcount position, then
+      // it walks the chain codes (5 instructions per segment)
+      const u32* ch = p.chain + (e_owner * S + s) * p.CW;
+      const int len = pe.len[s], r = (len + LPE - 1) >> sh;
+      int i = sub * r;
+      const int i1 = min(i + r, len);
+      if (i < i1) {
+        int pos = chain_pos(pe.head[s], pe.c0[s], ch, V, i);
+        u32 w = (i >> 4) ? ch[i >> 4] : pe.c0[s];  // the word holding the code of the move from segment i to i + 1
+        for (;;) {
+          put_pixel<S, K>(img + pos * C, s, i == 0, paint);
+          if (i + 1 >= i1) break;
+          pos -= chain_delta((w >> (2 * (i & 15))) & 3, V);
+          ++i;
+          if ((i & 15) == 0) w = ch[i >> 4];
+        }
+      }
+    }
+    if (s + 1 < S) __syncthreads();
+  }
+}
+
+template <int S, int RULES, int K>
+__global__ void __launch_bounds__(64) k_lane_paint2(const Params p) {
+  extern __shared__ __align__(128) u8 smem[];
+  __shared__ __align__(8) u64 s_bar;
+  const int tid = threadIdx.x, NT = 64;
+  const int TE = p.TE, LPE = NT / TE, E = p.E;
+  const int tile_bytes = TE * E;
+  u8* tile = smem;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_expect_tx(&s_bar, (u32)tile_bytes);
+    for (int c = 0; c < TE / p.G; ++c) bulk_load_g2s(tile + c * p.G * E, p.tmpl, (u32)(p.G * E), &s_bar);
+  }
+  __syncthreads();
+  const int slot = tid / LPE, sub = tid - slot * LPE;
+  u8* img = tile + slot * E;
+  const long long n_items = (p.N + TE - 1) / TE;
+  const long long stride = gridDim.x;
+  long long item = blockIdx.x;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the records of this step come from k_lane_logic
+  PaintEnv<S> cur = paint_env_from_memory<S>(p, item < n_items ? item * TE + slot : p.N);
+  mbar_wait(&s_bar, 0);
+  const int sh = 31 - __clz(LPE);
+  while (item < n_items) {
+    const long long next = item + stride;
+    const PaintEnv<S> nxt = paint_env_from_memory<S>(p, next < n_items ? next * TE + slot : p.N);
+    const long long e0 = item * TE;
+    int trips = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) trips += (cur.len[s] + LPE - 1) >> sh;
+    const bool restore = __syncthreads_or(p.restore_thr > 0 && trips > p.restore_thr);
+    cta_paint<S, RULES, K>(p, cur, e0 + slot, sub, LPE, img, true);
+    fence_async_smem();
+    __syncthreads();
+    if (p.N - e0 >= TE && p.store_mode == 0) {
+      if (tid == 0) {
+        u8* gdst = p.obs + e0 * (long long)E;
+        const u64 pol = l2_evict_first_policy();
+        for (int off = 0; off < tile_bytes; off += SNK_LANE_BULK) {
+          if (p.obs_evict_first) bulk_store_s2g_hint(gdst + off, tile + off, (u32)min(SNK_LANE_BULK, tile_bytes - off), pol);
+          else bulk_store_s2g(gdst + off, tile + off, (u32)min(SNK_LANE_BULK, tile_bytes - off));
+        }
+        bulk_commit();
+        bulk_wait_read();
+      }
+    } else {  // partial last image, or the STG experiment switch
+      u8* gdst = p.obs + e0 * (long long)E;
+      const long long left = p.N - e0;
+      const int bytes = (int)(left < TE ? left : TE) * E;
+      if (left >= TE) {
+        const uint4* src = reinterpret_cast<const uint4*>(tile);
+        uint4* dst = reinterpret_cast<uint4*>(gdst);
+        for (int i = tid; i < bytes / 16; i += NT) __stcs(dst + i, src[i]);
+      } else {
+        for (int i = tid; i < bytes; i += NT) gdst[i] = tile[i];
+      }
+    }
+    __syncthreads();
+    if (restore) cta_restore<K>(tile, tile_bytes >> 4, img, p.V, sub, LPE, tid, NT);
+    else cta_paint<S, RULES, K>(p, cur, e0 + slot, sub, LPE, img, false);
+    __syncthreads();
+    cur = nxt;
+    item = next;
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid == 0) bulk_wait_all();
 }
 
 
@@ -460,7 +620,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   __shared__ __align__(8) u64 s_bar[2];
   __shared__ u32 s_bm[2][SPAWN_WORDS];  // per warp: scratch of group_spawn
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpc = blockDim.x >> 5;
-  const int TE = p.TE, LPE = 32 / TE, E = p.E;
+  const int TE = p.TE, LPE = 32 / TE, E = p.E, EPW = p.EPW;  // EPW envs per warp batch: 32, fewer when the shard is small (snk_api.cu)
   const int tile_bytes = TE * E;
   u8* tile = smem + warp * p.tile_stride;
   // the border-only image arrives through the TMA engine while the first batch is being stepped
@@ -478,7 +638,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   u32 errs = 0;
   const int slot = lane / LPE, sub = lane - slot * LPE;
   u8* img = tile + slot * E;
-  const long long n_batches = (p.N + 31) / 32;
+  const long long n_batches = (p.N + EPW - 1) / EPW;
   const long long stride = (long long)gridDim.x * wpc;
   const bool stepping = p.mode == MODE_STEP;
   long long b = (long long)blockIdx.x * wpc + warp;
@@ -488,7 +648,7 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
   // output are only touched after the previous grid has completed and flushed.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   peer_push(p, tid);  // the running sums as of the previous step, to every peer (posted stores)
-  if (b < n_batches && b * 32 + lane < p.N) raw = lane_fetch<S>(p, b * 32 + lane, stepping);
+  if (b < n_batches && lane < EPW && b * EPW + lane < p.N) raw = lane_fetch<S>(p, b * EPW + lane, stepping);
   bool have_image = false;
 #ifdef SNK_PHASE_TIMING  // experiment build (tools/phase.py): cycles per phase, summed over warps
   long long tA = 0, tB = 0, tC = 0, tD = 0; const long long tStart = clock64();
@@ -497,8 +657,8 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
 #ifdef SNK_PHASE_TIMING
     long long t0 = clock64();
 #endif
-    const long long e = b * 32 + lane;
-    const bool valid = e < p.N;
+    const long long e = b * EPW + lane;
+    const bool valid = lane < EPW && e < p.N;  // lanes past EPW idle through the logic and join the painting
     LaneEnv<S> env;
 #pragma unroll
     for (int s = 0; s < S; ++s) { env.head[s] = 0; env.len[s] = 0; env.c0[s] = 0; env.grow[s] = 0; env.vel[s] = 0; }
@@ -517,15 +677,15 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
       if (valid && p.mode != MODE_OBSERVE) lane_store<S>(p, e, env);
     }
     // records + actions of this warp's NEXT batch: in flight while the current one is painted
-    if (b + stride < n_batches && (b + stride) * 32 + lane < p.N) raw = lane_fetch<S>(p, (b + stride) * 32 + lane, stepping);
+    if (b + stride < n_batches && lane < EPW && (b + stride) * EPW + lane < p.N) raw = lane_fetch<S>(p, (b + stride) * EPW + lane, stepping);
     const bool restore = lane_wants_restore<S>(p, env.len, LPE);  // one decision for the batch's 32/TE images
     if (!have_image) { mbar_wait(&s_bar[warp], 0); have_image = true; }
     __syncwarp();  // chain words / fruit grid written by the owner lane are read by the painting lanes
 #ifdef SNK_PHASE_TIMING
     { const long long t1 = clock64(); tA += t1 - t0; t0 = t1; }
 #endif
-    for (int q = 0; q < LPE; ++q) {
-      const long long e0 = b * 32 + (long long)q * TE;
+    for (int q = 0; q * TE < EPW; ++q) {
+      const long long e0 = b * EPW + (long long)q * TE;
       if (e0 >= p.N) break;
       const PaintEnv<S> pe = paint_env_from_lane<S>(env, valid, q * TE + slot);
       lane_paint<S, RULES, K>(p, pe, e0 + slot, sub, LPE, img, true);
@@ -937,19 +1097,59 @@ static cudaError_t launch_upscale(const uint8_t* native, uint8_t* out, long long
 
 
 // k_scripted_actions: greedy fruit seeking on the device (benchmark action stream).  One thread per
-// env; occupancy = bitmap over padded cell ids in local memory, filled by walking the chain codes.
+// env, registers only: the up-to-four candidate cells of every snake are compared against every
+// segment in ONE walk of the chain codes (the first form kept a V*V-bit occupancy bitmap in local
+// memory: 25 us per 131 072 envs, as long as a quarter of the step it feeds).
+// `occ_obs` (may be NULL): the native observations of the state the policy acts on.  A cell holds a snake segment or lies
+// outside the board exactly when the green byte of its pixel in view 0 is non-zero (snake_rgb / the white border; fruit
+// and empty cells have G = 0), so six byte loads replace the walk of both bodies -- which, one env per lane, cost every
+// warp its longest pair of snakes: 31 us per 131 072 envs under this policy, a third of the step it feeds.
 template <int S>
-__global__ void __launch_bounds__(128) k_scripted_actions(const Params p, int8_t* actions, u64 step, u64 seed, int eps_permille) {
+__global__ void __launch_bounds__(128) k_scripted_actions(const Params p, int8_t* actions, u64 step, u64 seed, int eps_permille,
+                                                          const u8* __restrict__ occ_obs) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // launched programmatically between two step kernels: wait for the step that produced the state, then let the next
+  // step's prologue in right away (it waits for this grid's completion itself before it touches the actions)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (e >= p.N) return;
   LaneEnv<S> env;
   lane_load<S>(p, e, env);
-  u32 occ[37];  // V*V <= 1156 bits
-  const int nW = (p.VV + 31) / 32, V = p.V, F = p.F;
-  for (int w = 0; w < nW; ++w) occ[w] = 0;
+  const int V = p.V, F = p.F;
+  int cand[S][4];   // cell a snake would enter with action a+1, or -1: not a candidate (dead, reversal, outside)
 #pragma unroll
-  for (int s = 0; s < S; ++s)
-    chain_walk(env.head[s], env.len[s], env.c0[s], p.chain + (e * S + s) * p.CW, V, [&](int, int pid) { occ[pid >> 5] |= 1u << (pid & 31); });
+  for (int s = 0; s < S; ++s) {
+#pragma unroll
+    for (int a = 1; a <= 4; ++a) {
+      int c = -1;
+      if (env.len[s] && !(env.vel[s] && a == (((env.vel[s] + 1) & 3) + 1))) {  // reversal is ignored by the env anyway
+        c = env.head[s] + chain_delta((u32)(a - 1), V);
+        if (!occ_obs && (__ldg(p.cellinfo + c) >> 31)) c = -1;  // (from the observations: the border's G byte blocks it below)
+      }
+      cand[s][a - 1] = c;
+    }
+  }
+  u32 blocked = 0;  // bit 4s + a-1: some segment of some snake lies on cand[s][a-1]
+  if (occ_obs) {
+    const u8* o = occ_obs + e * (long long)p.E + 1;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) if (cand[s][a] >= 0 && __ldg(o + cand[s][a] * p.C) != 0) blocked |= 1u << (4 * s + a);
+    }
+  } else
+#pragma unroll
+  for (int j = 0; j < S; ++j)
+    chain_walk(env.head[j], env.len[j], env.c0[j], p.chain + (e * S + j) * p.CW, V, [&](int, int pid) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) if (pid == cand[s][a]) blocked |= 1u << (4 * s + a);
+      }
+    });
+  int fx[4], fy[4];
+#pragma unroll
+  for (int f = 0; f < 4; ++f) { fx[f] = env.fruit[f] / V; fy[f] = env.fruit[f] - fx[f] * V; }
   u32 packed = 0;
 #pragma unroll
   for (int s = 0; s < S; ++s) {
@@ -960,15 +1160,15 @@ __global__ void __launch_bounds__(128) k_scripted_actions(const Params p, int8_t
         best = (int)(rnd % 5u);
       } else {
         int best_d = 0x7fffffff;
+#pragma unroll
         for (int a = 1; a <= 4; ++a) {
-          if (env.vel[s] && a == (((env.vel[s] + 1) & 3) + 1)) continue;  // reversal is ignored by the env anyway
-          const int c = env.head[s] + chain_delta((u32)(a - 1), V);
-          if ((__ldg(p.cellinfo + c) >> 31) || ((occ[c >> 5] >> (c & 31)) & 1)) continue;
+          const int c = cand[s][a - 1];
+          if (c < 0 || ((blocked >> (4 * s + a - 1)) & 1)) continue;
           const int cx = c / V, cy = c - cx * V;
           int d = 0x7ffffffe;
 #pragma unroll
           for (int f = 0; f < 4; ++f)
-            if (f < F) { const int fx = env.fruit[f] / V, fy = env.fruit[f] - fx * V; d = min(d, abs(cx - fx) + abs(cy - fy)); }
+            if (f < F) d = min(d, abs(cx - fx[f]) + abs(cy - fy[f]));
           if (d < best_d) { best_d = d; best = a; }
         }
       }
@@ -1197,9 +1397,23 @@ cudaError_t launch_rules(const Params& p, const LaunchPlan& plan, cudaStream_t s
       attr[0].val.programmaticStreamSerializationAllowed = plan.pdl ? 1 : 0;                                 \
       cfg.attrs = attr; cfg.numAttrs = 1;                                                                    \
       return cudaLaunchKernelEx(&cfg, k_step_lane<s, RULES, k>, p);                                          \
-    } else {                                                                                                 \
+    } else if (!plan.paint2) {                                                                               \
       if (p.mode != MODE_OBSERVE) k_lane_logic<s, RULES><<<(unsigned)((p.N + 127) / 128), 128, 0, stream>>>(p); \
       k_lane_paint<s, RULES, k><<<plan.grid, plan.block, plan.smem, stream>>>(p);                            \
+    } else {                                                                                                 \
+      cudaLaunchConfig_t cfg = {};                                                                           \
+      cfg.stream = stream;                                                                                   \
+      cudaLaunchAttribute attr[1];                                                                           \
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                       \
+      attr[0].val.programmaticStreamSerializationAllowed = plan.pdl ? 1 : 0;                                 \
+      cfg.attrs = attr; cfg.numAttrs = 1;                                                                    \
+      if (p.mode != MODE_OBSERVE) {                                                                          \
+        cfg.gridDim = dim3((unsigned)((p.N + 127) / 128)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; \
+        cudaError_t e1 = cudaLaunchKernelEx(&cfg, k_lane_logic<s, RULES>, p);                                \
+        if (e1 != cudaSuccess) return e1;                                                                    \
+      }                                                                                                      \
+      cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(plan.block); cfg.dynamicSmemBytes = plan.smem;      \
+      return cudaLaunchKernelEx(&cfg, k_lane_paint2<s, RULES, k>, p);                                        \
     }                                                                                                        \
     return cudaGetLastError();                                                                               \
   }
@@ -1244,6 +1458,10 @@ static cudaError_t plan_lane(LaunchPlan& plan, int& occ) {
   if (plan.ws) {
     if ((err = cudaFuncSetAttribute(k_step_lane_ws<S, RULES, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_step_lane_ws<S, RULES, K>, plan.block, plan.smem);
+  }
+  if (plan.split && plan.paint2) {
+    if ((err = cudaFuncSetAttribute(k_lane_paint2<S, RULES, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lane_paint2<S, RULES, K>, plan.block, plan.smem);
   }
   if (plan.split) {
     if ((err = cudaFuncSetAttribute(k_lane_paint<S, RULES, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem))) return err;
@@ -1334,13 +1552,19 @@ cudaError_t snk_launch_load(const Params& p, const u8* blob, const snk_state_lay
   return cudaGetLastError();
 }
 
-cudaError_t snk_launch_scripted_actions(const Params& p, int8_t* actions, u64 step, u64 seed, int eps_permille, cudaStream_t stream) {
-  const unsigned grid = (unsigned)((p.N + 127) / 128);
+cudaError_t snk_launch_scripted_actions(const Params& p, int8_t* actions, u64 step, u64 seed, int eps_permille, const uint8_t* occ_obs,
+                                        cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((p.N + 127) / 128)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
   switch (p.S) {
-    case 1: k_scripted_actions<1><<<grid, 128, 0, stream>>>(p, actions, step, seed, eps_permille); break;
-    case 2: k_scripted_actions<2><<<grid, 128, 0, stream>>>(p, actions, step, seed, eps_permille); break;
-    case 3: k_scripted_actions<3><<<grid, 128, 0, stream>>>(p, actions, step, seed, eps_permille); break;
-    default: k_scripted_actions<4><<<grid, 128, 0, stream>>>(p, actions, step, seed, eps_permille); break;
+    case 1: return cudaLaunchKernelEx(&cfg, k_scripted_actions<1>, p, actions, step, seed, eps_permille, occ_obs);
+    case 2: return cudaLaunchKernelEx(&cfg, k_scripted_actions<2>, p, actions, step, seed, eps_permille, occ_obs);
+    case 3: return cudaLaunchKernelEx(&cfg, k_scripted_actions<3>, p, actions, step, seed, eps_permille, occ_obs);
+    default: return cudaLaunchKernelEx(&cfg, k_scripted_actions<4>, p, actions, step, seed, eps_permille, occ_obs);
   }
   return cudaGetLastError();
 }

@@ -42,16 +42,22 @@ def short(N, T=400, reps=3, tag="short", **kw):
     g.close(); env.close()
 
 
-def long_(N, warm=400, T=100, **kw):
+def long_(N, warm=400, T=100, eps=0.05, **kw):
     """Fruit-seeking policy: policy kernel + step kernel (what bench.py's scripted_policy times), and the step kernel alone
     on the recorded actions from the same start state."""
     env = snakes_b200.SnakeVecEnv(N, **kw); env.reset()
-    gw = env.make_scripted_graph(warm, 0, 7); gw.launch(); gw.close()
+    gw = env.make_scripted_graph(warm, 0, 7, eps); gw.launch(); gw.close()
+    torch.cuda.synchronize()
+    for t in range(3):  # a few eager steps: the regime-adaptive path decides from the statistics the kernels post
+        env.step_async(env.gen_scripted_actions(warm + t, 7, eps)); env._pending = False
+    torch.cuda.synchronize()
+    warm += 3
     blob = env.dump_state_blob()
     acts = torch.empty((T, N, env.S), dtype=torch.int8, device="cuda")
     for t in range(T):
-        env.gen_scripted_actions(warm + t, 7, out=acts[t]); env.step_async(acts[t]); env._pending = False
-    gs = env.make_scripted_graph(T, warm, 7)
+        env.gen_scripted_actions(warm + t, 7, eps, out=acts[t]); env.step_async(acts[t]); env._pending = False
+    torch.cuda.synchronize()
+    gs = env.make_scripted_graph(T, warm, 7, eps)
     ga = env.make_graph(acts, T=T)
     both = step = 1e9
     for _ in range(3):
@@ -60,7 +66,7 @@ def long_(N, warm=400, T=100, **kw):
     for _ in range(3):
         env.load_state_blob(blob); env.reset_stats()
         step = min(step, timed_graph(env, ga, 1) / T * 1e3)
-    report("long  N=%d %s step only" % (N, kw), env, step, N)
+    report("long eps=%.2f N=%d %s step only" % (eps, N, kw), env, step, N)
     print("%-44s %8.2f us  (%.3e agent-steps/s)" % ("      policy kernel + step kernel", both, N * env.S / both * 1e6), flush=True)
     gs.close(); ga.close(); env.close()
 
@@ -69,7 +75,8 @@ if __name__ == "__main__":
     print("lib:", os.environ.get("SNK_LIB", "default"), " SNK_DEBUG:", os.environ.get("SNK_DEBUG", ""))
     which = sys.argv[1:] or ["short", "long"]
     if "short" in which: short(131072, size=19, n_snakes=2)
-    if "long" in which: long_(131072, size=19, n_snakes=2)
+    for w in which:
+        if w.startswith("long"): long_(131072, eps=(int(w[4:]) / 100.0 if len(w) > 4 else 0.05), size=19, n_snakes=2)
     if "c3" in which: short(65536, tag="c3", size=10, n_snakes=3, rules="cut")
     if "c3c" in which: short(65536, tag="c3 classic", size=10, n_snakes=3, rules="classic")
     if "c2" in which: short(4096, T=1000, tag="c2", size=10, n_snakes=2)
