@@ -301,6 +301,11 @@ int snk_launch_count(const snk_handle* h, uint64_t* out);
 /* The launch plan of the step kernel (bench.py's config.kernel): kind (0 lane, 1 tile, 2 dense, 3 rows), grid, block,
  * dynamic shared memory bytes, resident CTAs per SM, envs per CTA. */
 int snk_launch_info(const snk_handle* h, int32_t* out /*[6]*/);
+/* Which form of the lane path the NEXT step will launch (it follows the body-length regime):
+ * out[0] = 0 fused kernel, 1 warp-specialised kernel, 2 two kernels (k_lane_logic + k_lane_paint), 3 two kernels with
+ * k_lane_paint2, -1 not a lane-family configuration; out[1] = envs stepped per warp batch of the fused kernel;
+ * out[2] = envs per shared-memory image; out[3] = 1 when the handle switches forms by itself. */
+int snk_launch_form(const snk_handle* h, int32_t* out /*[4]*/);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,7 @@ _SIGNATURES = {
     "snk_algorithmic_bytes_per_step": (C.c_int, [C.POINTER(SnkConfig), C.c_double, C.POINTER(C.c_double)]),
     "snk_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "snk_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "snk_launch_form": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
 }
 
 _lib = None

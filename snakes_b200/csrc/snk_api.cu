@@ -1262,6 +1262,14 @@ extern "C" int snk_launch_count(const snk_handle* h, uint64_t* out) {
   return SNK_OK;
 }
 
+extern "C" int snk_launch_form(const snk_handle* h, int32_t* out /*[4]*/) {
+  if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
+  const LaunchPlan& pl = (h->have_alt && h->use_alt) ? h->plan_alt : h->plan;
+  out[0] = pl.kind != KIND_LANE ? -1 : pl.ws ? 1 : pl.split ? (pl.paint2 ? 3 : 2) : 0;
+  out[1] = pl.kind == KIND_LANE ? h->p.EPW : 0; out[2] = pl.kind == KIND_LANE ? h->p.TE : 0; out[3] = h->have_alt ? 1 : 0;
+  return SNK_OK;
+}
+
 extern "C" int snk_launch_info(const snk_handle* h, int32_t* out /*[6]: kind, grid, block, smem, occupancy, envs per CTA*/) {
   if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
   const LaunchPlan& pl = (h->have_alt && h->use_alt) ? h->plan_alt : h->plan;

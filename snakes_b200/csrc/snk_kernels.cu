@@ -301,8 +301,10 @@ template <int S, int RULES>
 __global__ void __launch_bounds__(128, (S <= 2 ? 7 : 1)) k_lane_logic(const Params p) {
   __shared__ double s_stats[SNK_NSTATS];
   __shared__ u32 s_bm[4][SPAWN_WORDS];  // per warp: scratch of group_spawn
+  __shared__ uint2 s_hop[256];          // displacements after 1..4 chain codes of a byte (lane_step<HOP>)
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < SNK_NSTATS) s_stats[tid] = 0.0;
+  build_hop_lut(s_hop, p.V, tid, 128);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous step's observation writer still reads the records
   peer_push(p, tid);  // the running sums as of the previous step, to every peer (posted stores)
   __syncthreads();
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(128, (S <= 2 ? 7 : 1)) k_lane_logic(const Para
     raw.act = 0;
     if (valid) { raw = lane_fetch<S>(p, e, p.mode == MODE_STEP); lane_unpack<S>(raw, env); }
     if (p.mode == MODE_STEP) {
-      lane_step<S, RULES>(p, e, valid, env, raw.act, rng, grid, s_bm[tid >> 5], errs, st);
+      lane_step<S, RULES, true>(p, e, valid, env, raw.act, rng, grid, s_bm[tid >> 5], errs, st, s_hop);
     } else if (valid && (!p.mask || p.mask[e])) {
       lane_reset<S, RULES>(p, e, env, rng, grid, errs, st.draws);
     }

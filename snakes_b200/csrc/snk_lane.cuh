@@ -341,9 +341,25 @@ struct LaneStats {
 // One env step in one lane (:166-197).
 // Called by ALL 32 lanes of the warp (the respawns are warp-cooperative); lanes without an env pass valid = false
 // and an env whose snakes all have length 0.  `bm` = SPAWN_WORDS words of shared memory private to the warp.
-template <int S, int RULES>
+//
+// HOP (the two-kernel form's k_lane_logic): the death test takes the chain codes four at a time.  A 256-entry table in
+// shared memory (build_hop_lut) holds, for every byte of codes, the displacement after one, two, three and four of them
+// as four 16-bit fields, so a group of four segments costs one 8-byte load, four subtractions and 4 S compares, with no
+// branch inside: 9 instructions per segment instead of 21 in the test that, one env per lane, costs every warp its
+// longest pair of snakes (43 % of the kernel's instructions under the fruit-seeking policy).  Same hits.
+__device__ __forceinline__ void build_hop_lut(uint2* lut, int V, int tid, int nthreads) {
+  for (int b = tid; b < 256; b += nthreads) {
+    int d = 0;
+    u32 f[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { d += chain_delta((u32)(b >> (2 * k)) & 3, V); f[k] = (u32)d & 0xffffu; }
+    lut[b] = make_uint2(f[0] | (f[1] << 16), f[2] | (f[3] << 16));
+  }
+}
+
+template <int S, int RULES, bool HOP = false>
 __device__ __forceinline__ void lane_step(const Params& p, long long e, bool valid, LaneEnv<S>& env, u32 act_packed, LaneRng& rng, const FruitSet& fs,
-                                          u32* bm, u32& errs, LaneStats& st) {
+                                          u32* bm, u32& errs, LaneStats& st, const uint2* hop_lut = nullptr) {
   const int V = p.V, F = p.F;
   const u32* chain_e = p.chain + e * S * p.CW;
   int act[S];
@@ -433,6 +449,32 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, bool val
   int live_head[S];  // head of a live snake, or an id no cell has: one compare per segment and snake in the walks
 #pragma unroll
   for (int s = 0; s < S; ++s) live_head[s] = env.len[s] ? env.head[s] : -1;
+  if (HOP) {
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      const u32* ch = chain_e + j * p.CW;
+      const int len = env.len[j];
+      int pid = env.head[j];
+      u32 w = env.c0[j];
+      for (int i = 0; i < len; i += 4) {
+        if ((i & 15) == 0 && i) w = ch[i >> 4];
+        const uint2 d = hop_lut[(w >> (2 * (i & 15))) & 0xffu];
+        const int n = len - i;  // segments i .. i+3 exist while k < n
+        const int q1 = pid - (int)(short)(d.x & 0xffffu), q2 = pid - ((int)d.x >> 16), q3 = pid - (int)(short)(d.y & 0xffffu);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int t = live_head[s];
+          const bool h0 = pid == t, h123 = (q1 == t && n > 1) || (q2 == t && n > 2) || (q3 == t && n > 3);
+          if (j == s) { if ((h0 && i) || h123) hit_own |= 1u << s; }
+          else {
+            if (h0 && !i) hit_head |= 1u << s;
+            if ((h0 && i) || h123) hit_body |= 1u << s;
+          }
+        }
+        pid -= (int)d.y >> 16;
+      }
+    }
+  } else {
 #pragma unroll
   for (int j = 0; j < S; ++j) {
     chain_walk(env.head[j], env.len[j], env.c0[j], chain_e + j * p.CW, V, [&](int i, int pid) {
@@ -445,6 +487,7 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, bool val
         }
       }
     });
+  }
   }
   u32 dead = empty | oob | hit_own | hit_head | hit_body;
   if (RULES == SNK_RULES_CUT) {

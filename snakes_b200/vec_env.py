@@ -634,7 +634,11 @@ class SnakeVecEnv(object):
         _lib.check(self._L.snk_launch_info(self._h, out))
         d = dict(zip(("kind", "grid", "block", "smem", "occupancy", "envs_per_cta"), list(out)))
         d["kernel"] = ("k_step_lane", "k_step_tile", "k_step_dense", "k_step_rows")[d["kind"]]
-        d["envs_per_cta"] = d["block"] if d["kind"] == 0 else d["envs_per_cta"]
+        f = (C.c_int32 * 4)()
+        _lib.check(self._L.snk_launch_form(self._h, f))
+        if d["kind"] == 0:  # the lane path has four forms; the handle may move between the first and the last by itself
+            d["kernel"] = ("k_step_lane", "k_step_lane_ws", "k_lane_logic + k_lane_paint", "k_lane_logic + k_lane_paint2")[f[0]]
+            d["envs_per_warp_batch"], d["envs_per_image"], d["adaptive"] = int(f[1]), int(f[2]), bool(f[3])
         return d
 
     def algorithmic_bytes_per_step(self, mean_sum_len):

@@ -333,7 +333,8 @@ def test_lane_restore_unpaint_matches_oracle(sb, thr, variant):
                                   ("adversarial", 3, 10, 300, 150), ("cut", 3, 14, 300, 150), ("classic", 4, 14, 100, 100)):
         kw = dict(size=D, n_snakes=S, rules=rules, seed=17)
         env = sb.SnakeVecEnv(N, debug=dbg, **kw)
-        assert env.launch_info()["kernel"] == "k_step_lane", (rules, S, D, env.launch_info())
+        assert env.launch_info()["kind"] == 0 and env.launch_info()["kernel"] == {
+            "fused": "k_step_lane", "ws": "k_step_lane_ws", "split": "k_lane_logic + k_lane_paint2"}[variant], (rules, S, D, env.launch_info())
         co = c_oracle.COracle(N, **kw)
         assert np.array_equal(env.reset().cpu().numpy(), co.reset())
         for t in range(steps):
