@@ -347,6 +347,48 @@ class SnakeVecEnv(object):
         self.step_async(actions)
         return self.step_wait()
 
+    # ------------------------------------------------------------------ pipelined host step, observations stay in HBM
+    def step_scalars_async(self, actions, depth=4):
+        """The step for a learner that lives on the GPU but is driven from the host (north_star: observations never
+        leave HBM): numpy `actions` [N][S] go through a pinned, NUMA-local slot to the device, the fused kernel steps,
+        and reward / done / num_snakes come back into the same slot's pinned arrays -- one C call (snk_step_host_async
+        without an observation buffer), nothing synchronises.  Up to `depth` steps may be in flight; the call blocks
+        only when the slot it is about to reuse has not completed yet.  Returns a ticket for `wait_scalars`.
+        The observations of the step are `self.obs` (device tensor, stream-ordered), or the rollout slot set with
+        set_obs_target / set_main_view_target."""
+        ring = getattr(self, "_ring", None)
+        if ring is None or len(ring) != depth:
+            if ring is not None:
+                torch.cuda.synchronize(self.device)
+                for sl in ring:
+                    for a in sl[:4]:
+                        self._L.snk_host_free(self._h, C.c_void_p(a.ctypes.data))
+            ring = self._ring = [(self._host_array((self.N, self.S), np.int8), self._host_array((self.N,), np.float32),
+                                  self._host_array((self.N,), np.uint8), self._host_array((self.N,), np.uint8),
+                                  torch.cuda.Event()) for _ in range(depth)]
+            self._ring_head = 0
+        if self._pending:
+            raise _lib.SnkError("already running an async step")
+        a, r, d, n, ev = ring[self._ring_head % depth]
+        ev.synchronize()   # the slot's previous trip (H2D read of `a`, D2H writes of r / d / n) is over
+        a[...] = np.asarray(actions).reshape(self.N, self.S)
+        self._before_overwrite()
+        p = lambda x: C.c_void_p(x.ctypes.data)
+        _lib.check(self._L.snk_step_host_async(self._h, p(a), None, 0, p(r), p(d), p(n), self._stream()))
+        ev.record(torch.cuda.current_stream(self.device))
+        self._ring_head += 1
+        return self._ring_head - 1
+
+    def wait_scalars(self, ticket):
+        """(reward float32 [N], done uint8 [N], num_snakes uint8 [N]) of the step `ticket`: views of its pinned slot,
+        valid until `depth` further steps have been enqueued."""
+        depth = len(self._ring)
+        if not self._ring_head - depth <= ticket < self._ring_head:
+            raise _lib.SnkError("ticket %d is no longer (or not yet) in the ring" % ticket)
+        _, r, d, n, ev = self._ring[ticket % depth]
+        ev.synchronize()
+        return r, d, n
+
     def close(self):
         if not getattr(self, "closed", True) and getattr(self, "_h", None):
             torch.cuda.synchronize(self.device)

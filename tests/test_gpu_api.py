@@ -125,6 +125,39 @@ def test_host_io_main_view_only(sb):
     full.close(); main.close()
 
 
+def test_step_scalars_pipeline(sb):
+    """Observations stay in HBM, actions in / scalars out through a ring of pinned slots with several steps in flight:
+    every ticket reports its own step (a slot is not reused before its trip is over) and the device state follows the
+    same trajectory as the plain device path."""
+    kw = dict(size=10, n_snakes=2, seed=5)
+    N, T, depth = 2048, 40, 3
+    ref = sb.SnakeVecEnv(N, **kw)
+    env = sb.SnakeVecEnv(N, **kw)
+    ref.reset(); env.reset()
+    acts = [ref.gen_actions(t, 11).cpu().numpy() for t in range(T)]
+    want = []
+    for t in range(T):
+        _, r, d, _ = ref.step(acts[t])
+        want.append((r.cpu().numpy(), d.cpu().numpy().astype(np.uint8), ref.num_alive.cpu().numpy()))
+    tickets, got = [], {}
+    for t in range(T):
+        tickets.append(env.step_scalars_async(acts[t], depth=depth))
+        if t >= depth - 1:   # read the oldest step still in the ring, `depth - 1` steps late
+            tk = tickets[t - depth + 1]
+            got[tk] = tuple(x.copy() for x in env.wait_scalars(tk))
+    with pytest.raises(sb.SnkError):
+        env.wait_scalars(tickets[0])          # long gone
+    for tk in tickets[-(depth - 1):]:
+        got[tk] = tuple(x.copy() for x in env.wait_scalars(tk))
+    for t in range(T):
+        r, d, n = got[tickets[t]]
+        assert r.dtype == np.float32 and np.array_equal(r, want[t][0]) and np.array_equal(d, want[t][1]) and np.array_equal(n, want[t][2]), t
+    assert np.array_equal(env.obs.cpu().numpy(), ref.obs.cpu().numpy())
+    a, b = env.dump_state(), ref.dump_state()
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    ref.close(); env.close()
+
+
 def test_infos_describe_their_own_step(sb):
     """An Infos object read AFTER the next step still reports its own step (SubprocVecEnv infos are immutable)."""
     N = 512
