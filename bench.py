@@ -509,9 +509,9 @@ def run_ours(args):
     d2h_main = N * env.V * env.V * 3 + N * 4 + 2 * N + 8 * N
 
     # obs stays in HBM for an on-device learner (north_star): numpy actions -> pinned slot -> H2D -> fused kernel ->
-    # reward + done + num_snakes D2H into the slot's pinned arrays, one C call per step (SnakeVecEnv.step_scalars_async),
-    # up to 4 steps in flight; every step's scalars are waited for and read (summed) one step late, as a learner's
-    # bookkeeping would
+    # reward + done + num_snakes + Monitor r/l D2H into the slot's pinned block, one C call per step
+    # (SnakeVecEnv.step_scalars_async), two steps in flight; every step's scalars are waited for and read one step late,
+    # as a learner's bookkeeping would
     Kr = Ke * 16
     env.reset()   # back to the headline regime (the scripted stream above left long snakes)
     for t in range(8):
@@ -522,7 +522,7 @@ def run_ours(args):
     for t in range(Kr):
         tk = env.step_scalars_async(h_acts[t % 8])
         if prev is not None:
-            rew, done, _ = env.wait_scalars(prev)
+            rew, done = env.wait_scalars(prev)[:2]
             acc += float(rew[0]) + float(done[0])
         prev = tk
     env.wait_scalars(prev)
@@ -580,10 +580,11 @@ def run_ours(args):
                               "pcie_gbs_per_gpu": (h2d + d2h_main) / e2e_main_s / 1e9,
                               "note": "host_views=1: only the main snake's view crosses PCIe (all the reference learner stores, "
                                       "ppo_multi_agent_new.py:181); the other views stay in HBM"},
-            "e2e_obs_resident": {"value": e2e_resident, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": N * 6,
+            "e2e_obs_resident": {"value": e2e_resident, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": N * 14,
                                  "steps": Kr, "note": "obs stays in HBM for an on-device learner (north_star); numpy actions H2D and reward + "
-                                                      "done + num_snakes D2H every step through pinned slots (SnakeVecEnv.step_scalars_async: "
-                                                      "one C call per step, 4 steps in flight, every step's scalars read one step late)"},
+                                                      "done + num_snakes + Monitor r/l D2H every step through two pinned slots, the copies on their own "
+                                                      "streams beside the step stream (SnakeVecEnv.step_scalars_async -> snk_step_scalars_async: "
+                                                      "one C call per step, two steps in flight, every step's scalars read one step late)"},
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_info["kernel"],

@@ -107,6 +107,10 @@ struct snk_handle {
   PeerArgs peer;               // ranks == 0: peer form not connected
   bool reduce_enabled;         // snk_comm_enable: A/B switch of the per-step reduction
   snk_graph* rollout_cache;    // the graph of the last snk_rollout call (re-launched when the arguments repeat)
+  // snk_step_scalars_async: two device slots (actions in, per-env scalars out) and the copy streams beside the step stream
+  struct ScalarSlot { int8_t* d_act; uint8_t* d_out; cudaEvent_t ev_in, ev_k, ev_out; bool used; } sc[2];
+  cudaStream_t s_in, s_out;
+  size_t sc_bytes, sc_off[5];  // block size; offsets of reward, done, num_alive, episode return, episode length
   std::string debug;
 };
 
@@ -272,6 +276,13 @@ extern "C" int snk_destroy(snk_handle* h) {
     if (h->cev_step[i]) cudaEventDestroy(h->cev_step[i]);
     if (h->cev_red[i]) cudaEventDestroy(h->cev_red[i]);
   }
+  for (int i = 0; i < 2; ++i) {
+    if (h->sc[i].ev_in) cudaEventDestroy(h->sc[i].ev_in);
+    if (h->sc[i].ev_k) cudaEventDestroy(h->sc[i].ev_k);
+    if (h->sc[i].ev_out) cudaEventDestroy(h->sc[i].ev_out);
+  }
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (void* q : h->allocs) cudaFree(q);
@@ -588,10 +599,13 @@ extern "C" int snk_get_buffers(const snk_handle* h, snk_buffers* out) {
   return SNK_OK;
 }
 
-struct RolloutSlot {  // per-step output redirection of a rollout graph
-  uint8_t* obs;
-  float* reward;
-  uint8_t* done;
+struct RolloutSlot {  // per-step output redirection (rollout graphs, snk_step_scalars_async); NULL = the handle's own buffer
+  uint8_t* obs = nullptr;
+  float* reward = nullptr;
+  uint8_t* done = nullptr;
+  uint8_t* alive = nullptr;
+  float* fin_ret = nullptr;
+  int32_t* fin_len = nullptr;
 };
 
 // One step (or reset / re-encode) on `stream`.  `capturing`: the call is being recorded into a CUDA graph (snk_graph_create);
@@ -624,6 +638,9 @@ static int launch(snk_handle* h, int mode, const int8_t* d_actions, const uint8_
   if (slot) {
     if (slot->reward) p.reward = slot->reward;
     if (slot->done) p.done = slot->done;
+    if (slot->alive) p.num_alive = slot->alive;
+    if (slot->fin_ret) p.fin_ret = slot->fin_ret;
+    if (slot->fin_len) p.fin_len = slot->fin_len;
     if (slot->obs) {
       obs_user = slot->obs;
       if (h->cfg.obs_mode != SNK_OBS_ATARI84) p.obs = slot->obs;
@@ -873,6 +890,82 @@ extern "C" int snk_step_host_views(snk_handle* h, const int8_t* h_actions, uint8
 extern "C" int snk_step_host_async(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, int32_t n_views_out, float* h_reward,
                                    uint8_t* h_done, uint8_t* h_num_alive, void* stream) {
   return step_host_impl(h, h_actions, h_obs, n_views_out, h_reward, h_done, h_num_alive, stream, false);
+}
+
+// ------------------------------------------------------------------ pipelined host step, observations stay in HBM
+// The learner sits on the GPU (north_star) but is driven from the host: per step it sends N*S action bytes and wants the
+// per-env scalars back.  On ONE stream that is H2D -> kernel -> D2H, each copy a PCIe round trip the next kernel waits
+// for (measured: 120 us per step around a 66 us kernel).  Here the copies run on two streams of their own and every step
+// writes its scalars into one of two device slots, so the step stream carries kernels only: the H2D of step t + 1 and the
+// D2H of step t - 1 overlap the kernel of step t.
+static void scalars_layout(const snk_handle* h, size_t* bytes, size_t off[5]) {
+  const size_t N = (size_t)h->p.N;
+  off[0] = 0;                          // reward          float [N]
+  off[1] = off[0] + align16(4 * N);    // done            uint8 [N]
+  off[2] = off[1] + align16(N);        // num_alive       uint8 [N]
+  off[3] = off[2] + align16(N);        // episode return  float [N]  (valid where done)
+  off[4] = off[3] + align16(4 * N);    // episode length  int32 [N]  (valid where done)
+  *bytes = off[4] + align16(4 * N);
+}
+
+extern "C" int snk_scalars_layout(const snk_handle* h, size_t* out) {
+  if (!h || !out) return fail(SNK_EINVAL, "NULL argument");
+  scalars_layout(h, &out[0], &out[1]);
+  return SNK_OK;
+}
+
+static int scalars_init(snk_handle* h) {
+  if (h->s_in) return SNK_OK;
+  scalars_layout(h, &h->sc_bytes, h->sc_off);
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    int rc;
+    if ((rc = dev_alloc(h, &h->sc[i].d_act, (size_t)h->p.N * h->p.S, true))) return rc;
+    if ((rc = dev_alloc(h, &h->sc[i].d_out, h->sc_bytes, true))) return rc;
+    CUDA_TRY(cudaEventCreateWithFlags(&h->sc[i].ev_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->sc[i].ev_k, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->sc[i].ev_out, cudaEventDisableTiming));
+    h->sc[i].used = false;
+  }
+  CUDA_TRY(cudaDeviceSynchronize());  // the memsets above ran on the legacy stream
+  return SNK_OK;
+}
+
+extern "C" int snk_step_scalars_async(snk_handle* h, const int8_t* h_actions, uint8_t* h_out, int32_t slot, void* stream) {
+  if (!h || !h_actions || !h_out || slot < 0 || slot > 1) return fail(SNK_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc = scalars_init(h);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  snk_handle::ScalarSlot& q = h->sc[slot];
+  const Params& p = h->p;
+  // actions: after the kernel that read this slot's action buffer two steps ago
+  if (q.used) CUDA_TRY(cudaStreamWaitEvent(h->s_in, q.ev_k, 0));
+  CUDA_TRY(cudaMemcpyAsync(q.d_act, h_actions, (size_t)p.N * p.S, cudaMemcpyHostToDevice, h->s_in));
+  CUDA_TRY(cudaEventRecord(q.ev_in, h->s_in));
+  CUDA_TRY(cudaStreamWaitEvent(s, q.ev_in, 0));
+  if (q.used) CUDA_TRY(cudaStreamWaitEvent(s, q.ev_out, 0));  // this slot's previous scalars have left the device
+  RolloutSlot rs;
+  rs.reward = reinterpret_cast<float*>(q.d_out + h->sc_off[0]);
+  rs.done = q.d_out + h->sc_off[1];
+  rs.alive = q.d_out + h->sc_off[2];
+  rs.fin_ret = reinterpret_cast<float*>(q.d_out + h->sc_off[3]);
+  rs.fin_len = reinterpret_cast<int32_t*>(q.d_out + h->sc_off[4]);
+  if ((rc = launch(h, MODE_STEP, q.d_act, nullptr, s, &rs))) return rc;
+  CUDA_TRY(cudaEventRecord(q.ev_k, s));
+  CUDA_TRY(cudaStreamWaitEvent(h->s_out, q.ev_k, 0));
+  CUDA_TRY(cudaMemcpyAsync(h_out, q.d_out, h->sc_bytes, cudaMemcpyDeviceToHost, h->s_out));
+  CUDA_TRY(cudaEventRecord(q.ev_out, h->s_out));
+  q.used = true;
+  return SNK_OK;
+}
+
+extern "C" int snk_scalars_wait(snk_handle* h, int32_t slot) {
+  if (!h || slot < 0 || slot > 1) return fail(SNK_EINVAL, "bad argument");
+  if (!h->s_in || !h->sc[slot].used) return SNK_OK;
+  CUDA_TRY(cudaEventSynchronize(h->sc[slot].ev_out));
+  return SNK_OK;
 }
 
 // Pinned host memory on the NUMA node the handle's GPU hangs off: with one process per GPU all writing ~350 MB of

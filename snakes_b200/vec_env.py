@@ -348,46 +348,45 @@ class SnakeVecEnv(object):
         return self.step_wait()
 
     # ------------------------------------------------------------------ pipelined host step, observations stay in HBM
-    def step_scalars_async(self, actions, depth=4):
+    def step_scalars_async(self, actions):
         """The step for a learner that lives on the GPU but is driven from the host (north_star: observations never
         leave HBM): numpy `actions` [N][S] go through a pinned, NUMA-local slot to the device, the fused kernel steps,
-        and reward / done / num_snakes come back into the same slot's pinned arrays -- one C call (snk_step_host_async
-        without an observation buffer), nothing synchronises.  Up to `depth` steps may be in flight; the call blocks
-        only when the slot it is about to reuse has not completed yet.  Returns a ticket for `wait_scalars`.
-        The observations of the step are `self.obs` (device tensor, stream-ordered), or the rollout slot set with
-        set_obs_target / set_main_view_target."""
+        and reward / done / num_snakes / Monitor r, l come back as ONE block into the slot's pinned memory
+        (snk_step_scalars_async: the copies run on streams of their own beside the step stream, so the H2D of the next
+        step and the D2H of the previous one overlap the kernel).  Nothing synchronises; two steps may be in flight, and
+        the call blocks only when the slot it is about to reuse (the step before last) has not arrived yet.  Returns a
+        ticket for `wait_scalars`.  The observations of the step are `self.obs` (device tensor, stream-ordered) or the
+        rollout slot set with set_obs_target / set_main_view_target; `self.rewards` etc. are NOT written."""
         ring = getattr(self, "_ring", None)
-        if ring is None or len(ring) != depth:
-            if ring is not None:
-                torch.cuda.synchronize(self.device)
-                for sl in ring:
-                    for a in sl[:4]:
-                        self._L.snk_host_free(self._h, C.c_void_p(a.ctypes.data))
-            ring = self._ring = [(self._host_array((self.N, self.S), np.int8), self._host_array((self.N,), np.float32),
-                                  self._host_array((self.N,), np.uint8), self._host_array((self.N,), np.uint8),
-                                  torch.cuda.Event()) for _ in range(depth)]
-            self._ring_head = 0
+        if ring is None:
+            lay = (C.c_size_t * 6)()
+            _lib.check(self._L.snk_scalars_layout(self._h, lay))
+            ring = []
+            for _ in range(2):
+                act = self._host_array((self.N, self.S), np.int8)
+                blk = self._host_array((int(lay[0]),), np.uint8)
+                part = lambda k, dt: blk[int(lay[1 + k]):int(lay[1 + k]) + self.N * np.dtype(dt).itemsize].view(dt)
+                ring.append((act, blk, (part(0, np.float32), part(1, np.uint8), part(2, np.uint8), part(3, np.float32), part(4, np.int32))))
+            self._ring, self._ring_head = ring, 0
         if self._pending:
             raise _lib.SnkError("already running an async step")
-        a, r, d, n, ev = ring[self._ring_head % depth]
-        ev.synchronize()   # the slot's previous trip (H2D read of `a`, D2H writes of r / d / n) is over
-        a[...] = np.asarray(actions).reshape(self.N, self.S)
+        slot = self._ring_head & 1
+        act, blk, _ = ring[slot]
+        _lib.check(self._L.snk_scalars_wait(self._h, slot))   # the slot's previous trip is over (H2D read, D2H written)
+        act[...] = np.asarray(actions).reshape(self.N, self.S)
         self._before_overwrite()
-        p = lambda x: C.c_void_p(x.ctypes.data)
-        _lib.check(self._L.snk_step_host_async(self._h, p(a), None, 0, p(r), p(d), p(n), self._stream()))
-        ev.record(torch.cuda.current_stream(self.device))
+        _lib.check(self._L.snk_step_scalars_async(self._h, C.c_void_p(act.ctypes.data), C.c_void_p(blk.ctypes.data), slot, self._stream()))
         self._ring_head += 1
         return self._ring_head - 1
 
     def wait_scalars(self, ticket):
-        """(reward float32 [N], done uint8 [N], num_snakes uint8 [N]) of the step `ticket`: views of its pinned slot,
-        valid until `depth` further steps have been enqueued."""
-        depth = len(self._ring)
-        if not self._ring_head - depth <= ticket < self._ring_head:
-            raise _lib.SnkError("ticket %d is no longer (or not yet) in the ring" % ticket)
-        _, r, d, n, ev = self._ring[ticket % depth]
-        ev.synchronize()
-        return r, d, n
+        """(reward float32, done uint8, num_snakes uint8, episode return float32, episode length int32), each [N], of the
+        step `ticket`: views of its pinned slot, valid until the step after next is enqueued.  The last two are Monitor's
+        r / l where done (monitor.py:62-76)."""
+        if not self._ring_head - 2 <= ticket < self._ring_head:
+            raise _lib.SnkError("ticket %d is no longer (or not yet) in flight" % ticket)
+        _lib.check(self._L.snk_scalars_wait(self._h, ticket & 1))
+        return self._ring[ticket & 1][2]
 
     def close(self):
         if not getattr(self, "closed", True) and getattr(self, "_h", None):

@@ -126,11 +126,11 @@ def test_host_io_main_view_only(sb):
 
 
 def test_step_scalars_pipeline(sb):
-    """Observations stay in HBM, actions in / scalars out through a ring of pinned slots with several steps in flight:
+    """Observations stay in HBM, actions in / scalars out through two pinned slots with the copies on their own streams:
     every ticket reports its own step (a slot is not reused before its trip is over) and the device state follows the
     same trajectory as the plain device path."""
     kw = dict(size=10, n_snakes=2, seed=5)
-    N, T, depth = 2048, 40, 3
+    N, T = 2048, 40
     ref = sb.SnakeVecEnv(N, **kw)
     env = sb.SnakeVecEnv(N, **kw)
     ref.reset(); env.reset()
@@ -138,20 +138,21 @@ def test_step_scalars_pipeline(sb):
     want = []
     for t in range(T):
         _, r, d, _ = ref.step(acts[t])
-        want.append((r.cpu().numpy(), d.cpu().numpy().astype(np.uint8), ref.num_alive.cpu().numpy()))
+        want.append((r.cpu().numpy(), d.cpu().numpy().astype(np.uint8), ref.num_alive.cpu().numpy(),
+                     ref.episode_return.cpu().numpy(), ref.episode_len.cpu().numpy()))
     tickets, got = [], {}
     for t in range(T):
-        tickets.append(env.step_scalars_async(acts[t], depth=depth))
-        if t >= depth - 1:   # read the oldest step still in the ring, `depth - 1` steps late
-            tk = tickets[t - depth + 1]
-            got[tk] = tuple(x.copy() for x in env.wait_scalars(tk))
+        tickets.append(env.step_scalars_async(acts[t]))
+        if t >= 1:   # read one step late, as a pipelined learner would
+            got[tickets[t - 1]] = tuple(x.copy() for x in env.wait_scalars(tickets[t - 1]))
     with pytest.raises(sb.SnkError):
         env.wait_scalars(tickets[0])          # long gone
-    for tk in tickets[-(depth - 1):]:
-        got[tk] = tuple(x.copy() for x in env.wait_scalars(tk))
+    got[tickets[-1]] = tuple(x.copy() for x in env.wait_scalars(tickets[-1]))
     for t in range(T):
-        r, d, n = got[tickets[t]]
+        r, d, n, er, el = got[tickets[t]]
         assert r.dtype == np.float32 and np.array_equal(r, want[t][0]) and np.array_equal(d, want[t][1]) and np.array_equal(n, want[t][2]), t
+        m = d.astype(bool)
+        assert np.array_equal(er[m], want[t][3][m]) and np.array_equal(el[m], want[t][4][m]), t
     assert np.array_equal(env.obs.cpu().numpy(), ref.obs.cpu().numpy())
     a, b = env.dump_state(), ref.dump_state()
     assert all(np.array_equal(a[k], b[k]) for k in a)
@@ -256,8 +257,11 @@ def test_main_view_target(sb):
     """snk_set_main_view_target: view 0 of every step, packed [N,H,W,3], lands in the caller's slot while all K views
     stay in the env's own buffer (f1: the learner's rollout keeps the main view only, ppo_multi_agent_new.py:181)."""
     import torch
-    for kw in (dict(size=19, n_snakes=2), dict(size=10, n_snakes=3, rules="cut"), dict(size=19, n_snakes=2, obs_mode="atari84")):
-        N = 203
+    cases = [(203, kw) for kw in (dict(size=19, n_snakes=2), dict(size=10, n_snakes=3, rules="cut"), dict(size=19, n_snakes=2, obs_mode="atari84"))]
+    # 16-byte aligned slots and whole 16-pixel groups: the vectorised gather (k_extract_main) for 6 / 9 / 12 bytes per pixel
+    cases += [(256, dict(size=19, n_snakes=2)), (256, dict(size=10, n_snakes=3, rules="cut")), (256, dict(size=10, n_snakes=4)),
+              (272, dict(size=19, n_snakes=2, obs_mode="atari84"))]
+    for N, kw in cases:
         env = sb.SnakeVecEnv(N, seed=5, **kw)
         H = env.obs.shape[1]
         slots = torch.zeros((5, N, H, H, 3), dtype=torch.uint8, device=env.device)

@@ -55,18 +55,18 @@ def main():
     name, ins = sass_lines(ksub)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, inst, seen = None, [], 0
+    # the report may hold several kernels: take the section whose SASS has as many instructions as the cubin's function
+    hdr, sections = None, []
     for r in rows:
         if len(r) >= 2 and r[0] == "Kernel Name":
-            seen += 1
-            if seen == 2:
-                break
+            sections.append([])
             continue
         if r and r[0] == "Address":
             hdr = r
             continue
-        if hdr and len(r) == len(hdr):
-            inst.append(r)
+        if hdr and sections and len(r) == len(hdr):
+            sections[-1].append(r)
+    inst = next((sec for sec in sections if len(sec) == len(ins)), sections[0] if sections else [])
     iI, iS, iSrc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
     assert len(inst) == len(ins), (len(inst), len(ins))
     by_line, by_line_s = {}, {}
