@@ -120,7 +120,7 @@ static int gcd(int a, int b) { return b ? gcd(b, a % b) : a; }
 // ---- experiment switches.  ONE string of comma-separated key=value pairs, given explicitly to snk_create_ex or, for
 // snk_create, read from the single environment variable SNK_DEBUG.  None changes results (all are parity-tested); an
 // unset / empty string is the production configuration.  Keys: force_kernel=lane|tile|rows|dense, lane=fused|ws|split,
-// store=stg, l2=<bits>, pdl=0, restore_thr=<n>, logic_warps=<n>, rows_kb=<n>, rows_block=<n>, extra_smem=<bytes>.
+// store=stg, restore=tma, l2=<bits>, pdl=0, restore_thr=<n>, logic_warps=<n>, rows_kb=<n>, rows_block=<n>, extra_smem=<bytes>.
 static bool dbg_get(const std::string& opts, const char* key, std::string* out) {
   size_t pos = 0;
   const size_t klen = strlen(key);
@@ -377,6 +377,7 @@ extern "C" int snk_create_ex(const snk_config* cfg, const char* debug_opts, snk_
   if (force == "lane" && !TE) { snk_destroy(h); return fail(SNK_EINVAL, "lane kernel does not support this configuration"); }
   p.family = plan.kind == KIND_LANE;
   p.store_mode = dbg_is(dbg, "store", "stg") ? 1 : 0;
+  p.restore_mode = dbg_is(dbg, "restore", "tma") ? 1 : 0;
   {  // L2 policies (l2 = bit0 obs evict-first, bit1 records evict-last)
     const int bits = dbg_int(dbg, "l2", 3);
     p.obs_evict_first = bits & 1; p.rec_evict_last = (bits >> 1) & 1;

@@ -51,6 +51,7 @@ struct Params {
   int R;                        // rows kernel: image rows per chunk buffer
   int PW;                       // warp-specialised lane kernel: paint warps per CTA (the others run game logic)
   u32 magicV, magicD;           // n / V == (n * magicV) >> 16 for n < V*V, n / D likewise for n < D*D (65536 / d + 1; exact while n * d < 65536)
+  int restore_mode;             // k_lane_paint2: how a long-body image buffer is restored: 0 = zero-fill + border redraw by the threads, 1 = TMA bulk load of the border template (experiment)
   int restore_thr;              // lane kernel: un-paint an image by zero-fill + border redraw when a lane would walk more segments than this (0 = always walk)
   int max_steps, auto_reset, rng_mode, mode;
   long long N, env_id_base, n_groups;

@@ -403,11 +403,43 @@ __device__ __forceinline__ void cta_restore(u8* tile, int n16, u8* img, int V, i
   }
 }
 
+// A lane's share of one image, worked out before any shared memory is touched: per snake the contiguous run
+// [i, i1) of segments this lane paints, the cell of segment i and the chain word holding the code that leads on from it.
+// Everything here reads global memory and registers only, so it runs while the TMA engine is still restoring the buffer.
+template <int S>
+struct PaintRuns {
+  int i[S], i1[S], pos[S];
+  u32 w[S];
+};
+template <int S>
+__device__ __forceinline__ PaintRuns<S> cta_paint_prepare(const Params& p, const PaintEnv<S>& pe, long long e_owner, int sub, int LPE) {
+  PaintRuns<S> r;
+  const int sh = 31 - __clz(LPE);
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    r.i[s] = r.i1[s] = 0; r.pos[s] = 0; r.w[s] = 0;
+    if (pe.valid) {
+      // lane `sub` takes the contiguous run [sub * n, sub * n + n) of the snake's segments: one popcount position, then
+      // it walks the chain codes (5 instructions per segment)
+      const u32* ch = p.chain + (e_owner * S + s) * p.CW;
+      const int len = pe.len[s], n = (len + LPE - 1) >> sh;
+      const int i = sub * n;
+      r.i[s] = i; r.i1[s] = min(i + n, len);
+      if (i < r.i1[s]) {
+        r.pos[s] = chain_pos(pe.head[s], pe.c0[s], ch, p.V, i);
+        r.w[s] = (i >> 4) ? ch[i >> 4] : pe.c0[s];  // the word holding the code of the move from segment i to i + 1
+      }
+    }
+  }
+  return r;
+}
+
 // fruits, then the snakes in index order (get_ob_for_snake :35-58); `paint` false = the same walk writes zeros
 template <int S, int RULES, int K>
-__device__ __forceinline__ void cta_paint(const Params& p, const PaintEnv<S>& pe, long long e_owner, int sub, int LPE, u8* img, bool paint) {
+__device__ __forceinline__ void cta_paint(const Params& p, const PaintEnv<S>& pe, const PaintRuns<S>& runs, long long e_owner, int sub, int LPE,
+                                          u8* img, bool paint) {
   constexpr int C = 3 * K;
-  const int V = p.V, F = p.F, sh = 31 - __clz(LPE);
+  const int V = p.V, F = p.F;
   const u8 red = paint ? 255 : 0;
   if (RULES == SNK_RULES_CLASSIC) {
 #pragma unroll
@@ -422,7 +454,9 @@ __device__ __forceinline__ void cta_paint(const Params& p, const PaintEnv<S>& pe
     for (int w = sub; w < p.GBW; w += LPE) {
       for (u32 bits = gb[w]; bits; bits &= bits - 1) {
         const int pid = 32 * w + __ffs(bits) - 1;
-        if (!(__ldg(p.cellinfo + pid) >> 31)) {
+        // cells outside the board lie under the border (the reference paints them, then the wall over them, :52-56)
+        const u32 px = ((u32)pid * p.magicV) >> 16, py = (u32)pid - px * (u32)V;
+        if (px - 1u < (u32)(V - 2) && py - 1u < (u32)(V - 2)) {
 #pragma unroll
           for (int k = 0; k < K; ++k) img[pid * C + 3 * k] = red;
         }
@@ -432,29 +466,28 @@ __device__ __forceinline__ void cta_paint(const Params& p, const PaintEnv<S>& pe
   __syncthreads();
 #pragma unroll
   for (int s = 0; s < S; ++s) {
-    if (pe.valid) {
-      // lane `sub` takes the contiguous run [sub * r, sub * r + r) of the snake's segments: one popcount position, then
-      // it walks the chain codes (5 instructions per segment)
+    if (runs.i[s] < runs.i1[s]) {
       const u32* ch = p.chain + (e_owner * S + s) * p.CW;
-      const int len = pe.len[s], r = (len + LPE - 1) >> sh;
-      int i = sub * r;
-      const int i1 = min(i + r, len);
-      if (i < i1) {
-        int pos = chain_pos(pe.head[s], pe.c0[s], ch, V, i);
-        u32 w = (i >> 4) ? ch[i >> 4] : pe.c0[s];  // the word holding the code of the move from segment i to i + 1
-        for (;;) {
-          put_pixel<S, K>(img + pos * C, s, i == 0, paint);
-          if (i + 1 >= i1) break;
-          pos -= chain_delta((w >> (2 * (i & 15))) & 3, V);
-          ++i;
-          if ((i & 15) == 0) w = ch[i >> 4];
-        }
+      int i = runs.i[s], pos = runs.pos[s];
+      const int i1 = runs.i1[s];
+      u32 w = runs.w[s];
+      for (;;) {
+        put_pixel<S, K>(img + pos * C, s, i == 0, paint);
+        if (i + 1 >= i1) break;
+        pos -= chain_delta((w >> (2 * (i & 15))) & 3, V);
+        ++i;
+        if ((i & 15) == 0) w = ch[i >> 4];
       }
     }
     if (s + 1 < S) __syncthreads();
   }
 }
 
+// Un-paint.  Short bodies: the same walk writes zeros.  Long bodies (`restore`): the threads zero-fill the buffer and redraw
+// the border (cta_restore), or -- restore=tma, an experiment that lost -- the TMA engine fetches the border-only image from
+// its L2-resident template back into the buffer while the CTA works on the global loads of its next image: no instructions
+// for a quarter of this kernel's instruction count, but the copy's latency is longer than the stores it replaces
+// (fruit-seeking stream 90.2 vs 88.7 us per step).  A CTA's last image is not un-painted at all.
 template <int S, int RULES, int K>
 __global__ void __launch_bounds__(64) k_lane_paint2(const Params p) {
   extern __shared__ __align__(128) u8 smem[];
@@ -476,8 +509,10 @@ __global__ void __launch_bounds__(64) k_lane_paint2(const Params p) {
   long long item = blockIdx.x;
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the records of this step come from k_lane_logic
   PaintEnv<S> cur = paint_env_from_memory<S>(p, item < n_items ? item * TE + slot : p.N);
-  mbar_wait(&s_bar, 0);
+  u32 phase = 0;        // parity of the mbarrier phase the buffer's next fill completes
+  bool filling = true;  // a bulk load into the buffer is in flight (the border image, later the restores)
   const int sh = 31 - __clz(LPE);
+  const bool tma_restore = p.restore_mode == 1;
   while (item < n_items) {
     const long long next = item + stride;
     const PaintEnv<S> nxt = paint_env_from_memory<S>(p, next < n_items ? next * TE + slot : p.N);
@@ -485,8 +520,10 @@ __global__ void __launch_bounds__(64) k_lane_paint2(const Params p) {
     int trips = 0;
 #pragma unroll
     for (int s = 0; s < S; ++s) trips += (cur.len[s] + LPE - 1) >> sh;
+    const PaintRuns<S> runs = cta_paint_prepare<S>(p, cur, e0 + slot, sub, LPE);
     const bool restore = __syncthreads_or(p.restore_thr > 0 && trips > p.restore_thr);
-    cta_paint<S, RULES, K>(p, cur, e0 + slot, sub, LPE, img, true);
+    if (filling) { mbar_wait(&s_bar, phase); phase ^= 1u; filling = false; }
+    cta_paint<S, RULES, K>(p, cur, runs, e0 + slot, sub, LPE, img, true);
     fence_async_smem();
     __syncthreads();
     if (p.N - e0 >= TE && p.store_mode == 0) {
@@ -499,6 +536,10 @@ __global__ void __launch_bounds__(64) k_lane_paint2(const Params p) {
         }
         bulk_commit();
         bulk_wait_read();
+        if (restore && tma_restore && next < n_items) {  // the engine has read the image: let it put the border image back
+          mbar_expect_tx(&s_bar, (u32)tile_bytes);
+          for (int c = 0; c < TE / p.G; ++c) bulk_load_g2s(tile + c * p.G * E, p.tmpl, (u32)(p.G * E), &s_bar);
+        }
       }
     } else {  // partial last image, or the STG experiment switch
       u8* gdst = p.obs + e0 * (long long)E;
@@ -511,16 +552,34 @@ __global__ void __launch_bounds__(64) k_lane_paint2(const Params p) {
       } else {
         for (int i = tid; i < bytes; i += NT) gdst[i] = tile[i];
       }
+      if (restore && tma_restore && next < n_items) {
+        __syncthreads();
+        if (tid == 0) {
+          mbar_expect_tx(&s_bar, (u32)tile_bytes);
+          for (int c = 0; c < TE / p.G; ++c) bulk_load_g2s(tile + c * p.G * E, p.tmpl, (u32)(p.G * E), &s_bar);
+        }
+      }
     }
-    __syncthreads();
-    if (restore) cta_restore<K>(tile, tile_bytes >> 4, img, p.V, sub, LPE, tid, NT);
-    else cta_paint<S, RULES, K>(p, cur, e0 + slot, sub, LPE, img, false);
-    __syncthreads();
+    if (next < n_items) {  // the last image of a CTA leaves its buffer as it is
+      if (restore && tma_restore) {
+        filling = true;  // waited for before the next paint; nobody touches the buffer until then
+      } else {
+        __syncthreads();
+        if (restore) cta_restore<K>(tile, tile_bytes >> 4, img, p.V, sub, LPE, tid, NT);
+        else cta_paint<S, RULES, K>(p, cur, runs, e0 + slot, sub, LPE, img, false);
+        __syncthreads();
+      }
+    }
     cur = nxt;
     item = next;
   }
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (filling) mbar_wait(&s_bar, phase);  // never leave with a bulk copy into our shared memory in flight
   if (tid == 0) bulk_wait_all();
+  // the dependent launch is released only once this CTA's images have left: with a policy kernel between two steps an
+  // earlier release (before the drain, or before the last un-paint that this kernel no longer does) cost 5 us per step
+  // (fruit-seeking stream 114.5 vs 109.1 us), and nothing without one (88.7 vs 89.2 us)
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 

@@ -62,6 +62,13 @@ def test_old_paint_kernel_still_matches(sb):
     _scripted_run(sb, 600, 120, "lane=split,paint2=0", dict(size=19, n_snakes=2, rules="classic", seed=2))
 
 
+def test_tma_restore_switch_still_matches(sb):
+    """restore=tma: the painter's long-body buffers are restored by a TMA bulk load of the border template instead of the
+    threads' zero-fill (a measured alternative that lost; kept selectable); ragged last image included."""
+    _scripted_run(sb, 601, 160, "lane=split,restore=tma", dict(size=19, n_snakes=2, rules="classic", seed=2))
+    _scripted_run(sb, 333, 120, "lane=split,restore=tma,restore_thr=1", dict(size=10, n_snakes=3, rules="classic", seed=6))
+
+
 def test_regime_switch_mid_run(sb):
     """adaptive lane path: threshold lowered so that the handle goes fused -> two kernels while the bodies grow and back
     when random actions shorten them again; every step bit-exact, both plans seen."""
