@@ -760,7 +760,9 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
 #ifdef SNK_PHASE_TIMING
       { const long long t1 = clock64(); tC += t1 - t0; t0 = t1; }
 #endif
-      lane_unpaint<S, RULES, K>(p, pe, e0 + slot, sub, LPE, tile, tile_bytes, img, lane, restore);
+      // the warp's last image of the launch leaves the buffer as it is (small shards: its only image)
+      if (b + stride < n_batches || ((q + 1) * TE < EPW && e0 + TE < p.N))
+        lane_unpaint<S, RULES, K>(p, pe, e0 + slot, sub, LPE, tile, tile_bytes, img, lane, restore);
       __syncwarp();
 #ifdef SNK_PHASE_TIMING
       { const long long t1 = clock64(); tD += t1 - t0; t0 = t1; }

@@ -1,1 +1,3 @@
-for m in 5 7 3; do SNK_DEBUG=restore_mode=$m python tools/ab.py long > gpurun_out/s8_mode$m.txt 2>&1; cut -c1-110 gpurun_out/s8_mode$m.txt; done
+python -m pytest tests/test_gpu_forms.py tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/s9_pytest.txt 2>&1; tail -2 gpurun_out/s9_pytest.txt
+SNK_LIB=variants/libsnk_base.so python tools/ab.py short c2 c3 > gpurun_out/s9_ab_base.txt 2>&1; cut -c1-110 gpurun_out/s9_ab_base.txt
+python tools/ab.py short c2 c3 long > gpurun_out/s9_ab_new.txt 2>&1; cut -c1-110 gpurun_out/s9_ab_new.txt
