@@ -361,7 +361,7 @@ def run_ours(args):
 
     # ---- headline: K steps = ONE graph launch
     K, W = args.steps, args.warmup
-    n_act = min(K, 256)  # distinct action batches resident in HBM, cycled
+    n_act = max(1, min(K, args.action_batches))  # distinct action batches resident in HBM, cycled
     acts = torch.empty((n_act, N, S), dtype=torch.int8, device=dev)
     for t in range(n_act):
         env.gen_actions(100 + t, 1, out=acts[t])
@@ -617,6 +617,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--action-batches", type=int, default=32,
+                    help="distinct pre-sampled action batches cycled by the timed steps (each N*S bytes, resident in HBM)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configurations")
