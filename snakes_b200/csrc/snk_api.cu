@@ -108,7 +108,7 @@ struct snk_handle {
   bool reduce_enabled;         // snk_comm_enable: A/B switch of the per-step reduction
   snk_graph* rollout_cache;    // the graph of the last snk_rollout call (re-launched when the arguments repeat)
   // snk_step_scalars_async: two device slots (actions in, per-env scalars out) and the copy streams beside the step stream
-  struct ScalarSlot { int8_t* d_act; uint8_t* d_out; cudaEvent_t ev_in, ev_k, ev_out; bool used; } sc[2];
+  struct ScalarSlot { int8_t* d_act; uint8_t* d_out; cudaEvent_t ev_in, ev_k, ev_out; bool used, host_synced; } sc[2];
   cudaStream_t s_in, s_out;
   size_t sc_bytes, sc_off[5];  // block size; offsets of reward, done, num_alive, episode return, episode length
   std::string debug;
@@ -941,12 +941,14 @@ extern "C" int snk_step_scalars_async(snk_handle* h, const int8_t* h_actions, ui
   cudaStream_t s = (cudaStream_t)stream;
   snk_handle::ScalarSlot& q = h->sc[slot];
   const Params& p = h->p;
-  // actions: after the kernel that read this slot's action buffer two steps ago
-  if (q.used) CUDA_TRY(cudaStreamWaitEvent(h->s_in, q.ev_k, 0));
+  // actions: after the kernel that read this slot's action buffer two steps ago (implied when the host has already
+  // waited for that step's scalars -- snk_scalars_wait -- as a caller that reuses the slot's host block must)
+  const bool ordered = !q.used || q.host_synced;
+  if (!ordered) CUDA_TRY(cudaStreamWaitEvent(h->s_in, q.ev_k, 0));
   CUDA_TRY(cudaMemcpyAsync(q.d_act, h_actions, (size_t)p.N * p.S, cudaMemcpyHostToDevice, h->s_in));
   CUDA_TRY(cudaEventRecord(q.ev_in, h->s_in));
   CUDA_TRY(cudaStreamWaitEvent(s, q.ev_in, 0));
-  if (q.used) CUDA_TRY(cudaStreamWaitEvent(s, q.ev_out, 0));  // this slot's previous scalars have left the device
+  if (!ordered) CUDA_TRY(cudaStreamWaitEvent(s, q.ev_out, 0));  // this slot's previous scalars have left the device
   RolloutSlot rs;
   rs.reward = reinterpret_cast<float*>(q.d_out + h->sc_off[0]);
   rs.done = q.d_out + h->sc_off[1];
@@ -958,7 +960,7 @@ extern "C" int snk_step_scalars_async(snk_handle* h, const int8_t* h_actions, ui
   CUDA_TRY(cudaStreamWaitEvent(h->s_out, q.ev_k, 0));
   CUDA_TRY(cudaMemcpyAsync(h_out, q.d_out, h->sc_bytes, cudaMemcpyDeviceToHost, h->s_out));
   CUDA_TRY(cudaEventRecord(q.ev_out, h->s_out));
-  q.used = true;
+  q.used = true; q.host_synced = false;
   return SNK_OK;
 }
 
@@ -966,6 +968,7 @@ extern "C" int snk_scalars_wait(snk_handle* h, int32_t slot) {
   if (!h || slot < 0 || slot > 1) return fail(SNK_EINVAL, "bad argument");
   if (!h->s_in || !h->sc[slot].used) return SNK_OK;
   CUDA_TRY(cudaEventSynchronize(h->sc[slot].ev_out));
+  h->sc[slot].host_synced = true;
   return SNK_OK;
 }
 

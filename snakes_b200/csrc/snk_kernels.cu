@@ -1110,36 +1110,67 @@ __device__ __forceinline__ void upscale_pixel(const u8* spx, u8* dst0, int C, in
   }
 }
 
+// The 84x84 image leaves in TWO parts (native rows [0, rows_a) and [rows_a, V); rows_a = V: one part), each its own bulk
+// group: while the engine streams part A out, the threads expand part B, and while B streams they expand part A of the
+// next env, whose native image was fetched into registers a whole env earlier.  The first form (expand the whole image,
+// hand it over, wait) left the SM's store path idle a third of the time: 1 070 us per 131 072 envs of 2 views 21x21
+// (5.5 TB/s) -- see DESIGN.md 4.11.
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
 template <int CT, int RT>
-__global__ void __launch_bounds__(256) k_upscale84(const u8* __restrict__ native, u8* __restrict__ out, long long N, int V, int C_) {
+__global__ void __launch_bounds__(256) k_upscale84(const u8* __restrict__ native, u8* __restrict__ out, long long N, int V, int C_, int rows_a) {
   extern __shared__ __align__(128) u8 smem[];
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = threadIdx.x, nthr = 256;
   const int C = CT > 0 ? CT : C_, r = RT > 0 ? RT : 84 / V;
   const int E = V * V * C, OUT = 84 * 84 * C;
   u8* dst = smem;
   u8* src = smem + ((OUT + 127) & ~127);
-  for (long long e = blockIdx.x; e < N; e += gridDim.x) {
-    const u8* g = native + e * (long long)E;
-    if ((E & 1) == 0) {
-      const u16* g16 = reinterpret_cast<const u16*>(g);
+  // halfwords of one native image per thread, known at compile time for the specialised shapes (V = 84 / RT)
+  constexpr int PF = (CT > 0 && RT > 0 && ((84 / (RT > 0 ? RT : 1)) * (84 / (RT > 0 ? RT : 1)) * CT) % 2 == 0)
+                         ? ((84 / (RT > 0 ? RT : 1)) * (84 / (RT > 0 ? RT : 1)) * CT / 2 + 255) / 256 : 0;
+  u16 pf[PF > 0 ? PF : 1];
+  const bool two = rows_a < V;
+  const int px_a = rows_a * V, bytes_a = rows_a * r * 84 * C;
+  long long e = blockIdx.x;
+  if (PF > 0 && e < N) {
+    const u16* g16 = reinterpret_cast<const u16*>(native + e * (long long)E);
+#pragma unroll
+    for (int k = 0; k < PF; ++k) { const int i = tid + k * nthr; pf[k] = i < E / 2 ? g16[i] : (u16)0; }
+  }
+  for (; e < N; e += gridDim.x) {
+    if (PF > 0) {
       u16* s16 = reinterpret_cast<u16*>(src);
-      for (int i = tid; i < E / 2; i += nthr) s16[i] = g16[i];
+#pragma unroll
+      for (int k = 0; k < PF; ++k) { const int i = tid + k * nthr; if (i < E / 2) s16[i] = pf[k]; }
+      const long long en = e + gridDim.x;
+      if (en < N) {  // the next env's native image: in flight while this one is expanded and streamed
+        const u16* g16 = reinterpret_cast<const u16*>(native + en * (long long)E);
+#pragma unroll
+        for (int k = 0; k < PF; ++k) { const int i = tid + k * nthr; pf[k] = i < E / 2 ? g16[i] : (u16)0; }
+      }
     } else {
+      const u8* g = native + e * (long long)E;
       for (int i = tid; i < E; i += nthr) src[i] = g[i];
     }
-    if (tid == 0) bulk_wait_read();  // the previous image has left shared memory
-    __syncthreads();
-    for (int sp = tid; sp < V * V; sp += nthr) {
-      const int x = sp / V, y = sp - x * V;
-      upscale_pixel<CT, RT>(src + sp * C, dst + ((x * r) * 84 + y * r) * C, C, r);
+    for (int part = 0; part < (two ? 2 : 1); ++part) {
+      // the part's region of the image buffer was last read by the bulk group issued two groups ago
+      if (tid == 0) { if (two) bulk_wait_read1(); else bulk_wait_read(); }
+      __syncthreads();  // also: src is complete
+      const int p0 = part ? px_a : 0, p1 = (two && !part) ? px_a : V * V;
+      for (int sp = p0 + tid; sp < p1; sp += nthr) {
+        const int x = sp / V, y = sp - x * V;
+        upscale_pixel<CT, RT>(src + sp * C, dst + ((x * r) * 84 + y * r) * C, C, r);
+      }
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        const int o0 = part ? bytes_a : 0, o1 = (two && !part) ? bytes_a : OUT;
+        u8* gd = out + e * (long long)OUT;
+        for (int off = o0; off < o1; off += 16384) bulk_store_s2g(gd + off, dst + off, (u32)min(16384, o1 - off));
+        bulk_commit();
+      }
     }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      u8* gd = out + e * (long long)OUT;
-      for (int off = 0; off < OUT; off += 16384) bulk_store_s2g(gd + off, dst + off, (u32)min(16384, OUT - off));
-      bulk_commit();
-    }
+    // (the barrier before the last part's hand-over also ended every read of src: the next iteration may overwrite it)
   }
   if (tid == 0) bulk_wait_all();
 }
@@ -1154,7 +1185,13 @@ static cudaError_t launch_upscale(const uint8_t* native, uint8_t* out, long long
   if (occ < 1) return cudaErrorInvalidConfiguration;
   long long grid = (long long)n_sm * occ;
   if (grid > N) grid = N;
-  k_upscale84<CT, RT><<<(unsigned)grid, 256, smem, stream>>>(native, out, N, V, C);
+  // two parts: the split nearest the middle whose first part is a whole number of 16-byte units (TMA); none: one part
+  const int r = 84 / V;
+  int rows_a = V;
+  for (int d = 0; d < V / 2 && rows_a == V; ++d)
+    for (int k : {V / 2 + d, V / 2 - d})
+      if (k > 0 && k < V && ((size_t)k * r * 84 * C) % 16 == 0) { rows_a = k; break; }
+  k_upscale84<CT, RT><<<(unsigned)grid, 256, smem, stream>>>(native, out, N, V, C, rows_a);
   return cudaGetLastError();
 }
 

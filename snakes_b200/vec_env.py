@@ -373,7 +373,7 @@ class SnakeVecEnv(object):
         slot = self._ring_head & 1
         act, blk, _ = ring[slot]
         _lib.check(self._L.snk_scalars_wait(self._h, slot))   # the slot's previous trip is over (H2D read, D2H written)
-        act[...] = np.asarray(actions).reshape(self.N, self.S)
+        np.copyto(act, np.asarray(actions).reshape(self.N, self.S), casting="unsafe")
         self._before_overwrite()
         _lib.check(self._L.snk_step_scalars_async(self._h, C.c_void_p(act.ctypes.data), C.c_void_p(blk.ctypes.data), slot, self._stream()))
         self._ring_head += 1

@@ -392,6 +392,24 @@ def test_atari84_obs_mode(sb, D, S, K, rules):
         sb.SnakeVecEnv(4, size=9, obs_mode="atari84")
 
 
+@pytest.mark.parametrize("D,S,K", [(19, 2, 2), (10, 3, 3), (19, 2, 3)])
+def test_atari84_many_envs_per_cta(sb, D, S, K):
+    """More envs than resident CTAs: every CTA of k_upscale84 streams several images through its two-part pipeline
+    (part B of env e and part A of env e + grid overlap; the next native image travels in registers)."""
+    N = 4001
+    kw = dict(size=D, n_snakes=S, n_views=K, rules="classic", seed=6)
+    env = sb.SnakeVecEnv(N, obs_mode="atari84", **kw)
+    nat = sb.SnakeVecEnv(N, **kw)
+    r = 84 // (D + 2)
+    up = lambda o: o.repeat_interleave(r, dim=1).repeat_interleave(r, dim=2)
+    import torch
+    assert torch.equal(env.reset(), up(nat.reset()))
+    for t in range(5):
+        a = nat.gen_actions(t, 8)
+        assert torch.equal(env.step(a)[0], up(nat.step(a)[0])), t
+    env.close(); nat.close()
+
+
 @pytest.mark.parametrize("rules,S,D", [("classic", 2, 19), ("adversarial", 3, 10), ("cut", 16, 64)])
 def test_checkpoint_resume_is_bit_exact(sb, tmp_path, rules, S, D):
     """save() / load(): the resumed env continues exactly like the original (state incl. RNG counters)."""
