@@ -785,6 +785,9 @@ static int graph_create_impl(snk_handle* h, const int8_t* d_actions, int32_t n_b
   if (ce != cudaSuccess) { snk_graph_destroy(g); return fail(SNK_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce)); }
   ce = cudaGraphInstantiate(&g->exec, g->graph, 0);
   if (ce != cudaSuccess) { snk_graph_destroy(g); return fail(SNK_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+  // move the executable graph to the device now, not inside the caller's first launch (a short rollout would pay it per step)
+  if (cudaGraphUpload(g->exec, h->cap_stream) == cudaSuccess) cudaStreamSynchronize(h->cap_stream);
+  cudaGetLastError();
   *out = g;
   return SNK_OK;
 }
