@@ -510,7 +510,7 @@ def run_ours(args):
 
     # obs stays in HBM for an on-device learner (north_star): numpy actions -> pinned slot -> H2D -> fused kernel ->
     # reward + done + num_snakes + Monitor r/l D2H into the slot's pinned block, one C call per step
-    # (SnakeVecEnv.step_scalars_async), two steps in flight; every step's scalars are waited for and read one step late,
+    # (SnakeVecEnv.step_scalars_async), up to four steps in flight; every step's scalars are waited for and read two steps late,
     # as a learner's bookkeeping would
     Kr = Ke * 16
     env.reset()   # back to the headline regime (the scripted stream above left long snakes)
@@ -518,14 +518,15 @@ def run_ours(args):
         env.wait_scalars(env.step_scalars_async(h_acts[t % 8]))
     barrier()
     t0 = time.perf_counter()
-    acc, prev = 0.0, None
+    acc, tickets = 0.0, []
     for t in range(Kr):
-        tk = env.step_scalars_async(h_acts[t % 8])
-        if prev is not None:
-            rew, done = env.wait_scalars(prev)[:2]
+        tickets.append(env.step_scalars_async(h_acts[t % 8]))
+        if t >= 2:   # every step's scalars are read, two steps late
+            rew, done = env.wait_scalars(tickets[t - 2])[:2]
             acc += float(rew[0]) + float(done[0])
-        prev = tk
-    env.wait_scalars(prev)
+    for tk in tickets[-2:]:
+        rew, done = env.wait_scalars(tk)[:2]
+        acc += float(rew[0]) + float(done[0])
     torch.cuda.synchronize(dev)
     e2e_resident = float(N) * world * Kr * S / max_over_ranks(time.perf_counter() - t0)
 
@@ -582,9 +583,9 @@ def run_ours(args):
                                       "ppo_multi_agent_new.py:181); the other views stay in HBM"},
             "e2e_obs_resident": {"value": e2e_resident, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": N * 14,
                                  "steps": Kr, "note": "obs stays in HBM for an on-device learner (north_star); numpy actions H2D and reward + "
-                                                      "done + num_snakes + Monitor r/l D2H every step through two pinned slots, the copies on their own "
+                                                      "done + num_snakes + Monitor r/l D2H every step through four pinned slots, the copies on their own "
                                                       "streams beside the step stream (SnakeVecEnv.step_scalars_async -> snk_step_scalars_async: "
-                                                      "one C call per step, two steps in flight, every step's scalars read one step late)"},
+                                                      "one C call per step, up to four steps in flight, every step's scalars read two steps late)"},
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_info["kernel"],

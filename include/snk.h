@@ -170,9 +170,9 @@ int snk_step_host_async(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, 
                         uint8_t* h_done, uint8_t* h_num_alive, void* stream);
 
 /* The same step for a learner that keeps the observations in HBM (north_star) but is driven from the host: N*S action
- * bytes in, the per-env scalars out, nothing else crosses PCIe.  Two slots (slot = step index & 1) let the copies run on
- * streams of their own beside the step stream: the H2D of step t+1 and the D2H of step t-1 overlap the kernel of step t,
- * so `stream` carries kernels only.  h_out (pinned, snk_scalars_layout bytes) receives ONE block per step:
+ * bytes in, the per-env scalars out, nothing else crosses PCIe.  SNK_SCALAR_SLOTS slots (slot = step index modulo the
+ * slots the caller uses, at least 2) let the copies run on streams of their own beside the step stream: the H2D of step
+ * t+1 and the D2H of step t-1 overlap the kernel of step t, so `stream` carries kernels only.  h_out (pinned, snk_scalars_layout bytes) receives ONE block per step:
  *   reward float[N] | done uint8[N] | num_alive uint8[N] | episode return float[N] | episode length int32[N]
  * (the last two valid where done: Monitor's r / l), each part 16-byte aligned at the offsets snk_scalars_layout reports
  * (out[0] = block bytes, out[1..5] = offsets in that order).  The call returns at once; snk_scalars_wait(slot) blocks
@@ -181,6 +181,7 @@ int snk_step_host_async(snk_handle* h, const int8_t* h_actions, uint8_t* h_obs, 
  * These steps write the observations as usual (handle buffer / snk_set_obs_target) but NOT the handle's own scalar
  * buffers of snk_get_buffers.  Replaces the `obs, rewards, dones, infos = env.step(actions)` round trip of Runner.run
  * (ppo_multi_agent_new.py:186-192) for an on-device learner. */
+#define SNK_SCALAR_SLOTS 4
 int snk_scalars_layout(const snk_handle* h, size_t* out /*[6]*/);
 int snk_step_scalars_async(snk_handle* h, const int8_t* h_actions, uint8_t* h_out, int32_t slot, void* stream);
 int snk_scalars_wait(snk_handle* h, int32_t slot);

@@ -107,8 +107,8 @@ struct snk_handle {
   PeerArgs peer;               // ranks == 0: peer form not connected
   bool reduce_enabled;         // snk_comm_enable: A/B switch of the per-step reduction
   snk_graph* rollout_cache;    // the graph of the last snk_rollout call (re-launched when the arguments repeat)
-  // snk_step_scalars_async: two device slots (actions in, per-env scalars out) and the copy streams beside the step stream
-  struct ScalarSlot { int8_t* d_act; uint8_t* d_out; cudaEvent_t ev_in, ev_k, ev_out; bool used, host_synced; } sc[2];
+  // snk_step_scalars_async: device slots (actions in, per-env scalars out) and the copy streams beside the step stream
+  struct ScalarSlot { int8_t* d_act; uint8_t* d_out; cudaEvent_t ev_in, ev_k, ev_out; bool used, host_synced; } sc[SNK_SCALAR_SLOTS];
   cudaStream_t s_in, s_out;
   size_t sc_bytes, sc_off[5];  // block size; offsets of reward, done, num_alive, episode return, episode length
   std::string debug;
@@ -276,7 +276,7 @@ extern "C" int snk_destroy(snk_handle* h) {
     if (h->cev_step[i]) cudaEventDestroy(h->cev_step[i]);
     if (h->cev_red[i]) cudaEventDestroy(h->cev_red[i]);
   }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < SNK_SCALAR_SLOTS; ++i) {
     if (h->sc[i].ev_in) cudaEventDestroy(h->sc[i].ev_in);
     if (h->sc[i].ev_k) cudaEventDestroy(h->sc[i].ev_k);
     if (h->sc[i].ev_out) cudaEventDestroy(h->sc[i].ev_out);
@@ -900,8 +900,9 @@ extern "C" int snk_step_host_async(snk_handle* h, const int8_t* h_actions, uint8
 // The learner sits on the GPU (north_star) but is driven from the host: per step it sends N*S action bytes and wants the
 // per-env scalars back.  On ONE stream that is H2D -> kernel -> D2H, each copy a PCIe round trip the next kernel waits
 // for (measured: 120 us per step around a 66 us kernel).  Here the copies run on two streams of their own and every step
-// writes its scalars into one of two device slots, so the step stream carries kernels only: the H2D of step t + 1 and the
-// D2H of step t - 1 overlap the kernel of step t.
+// writes its scalars into one of SNK_SCALAR_SLOTS device slots, so the step stream carries kernels only: the H2D of step
+// t + 1 and the D2H of step t - 1 overlap the kernel of step t, and a host that reads a step's scalars two steps late
+// never waits for the device.
 static void scalars_layout(const snk_handle* h, size_t* bytes, size_t off[5]) {
   const size_t N = (size_t)h->p.N;
   off[0] = 0;                          // reward          float [N]
@@ -923,7 +924,7 @@ static int scalars_init(snk_handle* h) {
   scalars_layout(h, &h->sc_bytes, h->sc_off);
   CUDA_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < SNK_SCALAR_SLOTS; ++i) {
     int rc;
     if ((rc = dev_alloc(h, &h->sc[i].d_act, (size_t)h->p.N * h->p.S, true))) return rc;
     if ((rc = dev_alloc(h, &h->sc[i].d_out, h->sc_bytes, true))) return rc;
@@ -937,7 +938,7 @@ static int scalars_init(snk_handle* h) {
 }
 
 extern "C" int snk_step_scalars_async(snk_handle* h, const int8_t* h_actions, uint8_t* h_out, int32_t slot, void* stream) {
-  if (!h || !h_actions || !h_out || slot < 0 || slot > 1) return fail(SNK_EINVAL, "bad argument");
+  if (!h || !h_actions || !h_out || slot < 0 || slot >= SNK_SCALAR_SLOTS) return fail(SNK_EINVAL, "bad argument");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   int rc = scalars_init(h);
   if (rc) return rc;
@@ -968,7 +969,7 @@ extern "C" int snk_step_scalars_async(snk_handle* h, const int8_t* h_actions, ui
 }
 
 extern "C" int snk_scalars_wait(snk_handle* h, int32_t slot) {
-  if (!h || slot < 0 || slot > 1) return fail(SNK_EINVAL, "bad argument");
+  if (!h || slot < 0 || slot >= SNK_SCALAR_SLOTS) return fail(SNK_EINVAL, "bad argument");
   if (!h->s_in || !h->sc[slot].used) return SNK_OK;
   CUDA_TRY(cudaEventSynchronize(h->sc[slot].ev_out));
   h->sc[slot].host_synced = true;

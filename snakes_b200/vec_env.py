@@ -348,13 +348,14 @@ class SnakeVecEnv(object):
         return self.step_wait()
 
     # ------------------------------------------------------------------ pipelined host step, observations stay in HBM
+    SCALAR_SLOTS = 4   # SNK_SCALAR_SLOTS of include/snk.h
     def step_scalars_async(self, actions):
         """The step for a learner that lives on the GPU but is driven from the host (north_star: observations never
         leave HBM): numpy `actions` [N][S] go through a pinned, NUMA-local slot to the device, the fused kernel steps,
         and reward / done / num_snakes / Monitor r, l come back as ONE block into the slot's pinned memory
         (snk_step_scalars_async: the copies run on streams of their own beside the step stream, so the H2D of the next
-        step and the D2H of the previous one overlap the kernel).  Nothing synchronises; two steps may be in flight, and
-        the call blocks only when the slot it is about to reuse (the step before last) has not arrived yet.  Returns a
+        step and the D2H of the previous one overlap the kernel).  Nothing synchronises; four steps may be in flight, and
+        the call blocks only when the slot it is about to reuse (four steps back) has not arrived yet.  Returns a
         ticket for `wait_scalars`.  The observations of the step are `self.obs` (device tensor, stream-ordered) or the
         rollout slot set with set_obs_target / set_main_view_target; `self.rewards` etc. are NOT written."""
         ring = getattr(self, "_ring", None)
@@ -362,7 +363,7 @@ class SnakeVecEnv(object):
             lay = (C.c_size_t * 6)()
             _lib.check(self._L.snk_scalars_layout(self._h, lay))
             ring = []
-            for _ in range(2):
+            for _ in range(self.SCALAR_SLOTS):
                 act = self._host_array((self.N, self.S), np.int8)
                 blk = self._host_array((int(lay[0]),), np.uint8)
                 part = lambda k, dt: blk[int(lay[1 + k]):int(lay[1 + k]) + self.N * np.dtype(dt).itemsize].view(dt)
@@ -370,7 +371,7 @@ class SnakeVecEnv(object):
             self._ring, self._ring_head = ring, 0
         if self._pending:
             raise _lib.SnkError("already running an async step")
-        slot = self._ring_head & 1
+        slot = self._ring_head % self.SCALAR_SLOTS
         act, blk, _ = ring[slot]
         _lib.check(self._L.snk_scalars_wait(self._h, slot))   # the slot's previous trip is over (H2D read, D2H written)
         np.copyto(act, np.asarray(actions).reshape(self.N, self.S), casting="unsafe")
@@ -381,12 +382,12 @@ class SnakeVecEnv(object):
 
     def wait_scalars(self, ticket):
         """(reward float32, done uint8, num_snakes uint8, episode return float32, episode length int32), each [N], of the
-        step `ticket`: views of its pinned slot, valid until the step after next is enqueued.  The last two are Monitor's
-        r / l where done (monitor.py:62-76)."""
-        if not self._ring_head - 2 <= ticket < self._ring_head:
+        step `ticket`: views of its pinned slot, valid until three further steps have been enqueued.  The last two are
+        Monitor's r / l where done (monitor.py:62-76)."""
+        if not self._ring_head - self.SCALAR_SLOTS <= ticket < self._ring_head:
             raise _lib.SnkError("ticket %d is no longer (or not yet) in flight" % ticket)
-        _lib.check(self._L.snk_scalars_wait(self._h, ticket & 1))
-        return self._ring[ticket & 1][2]
+        _lib.check(self._L.snk_scalars_wait(self._h, ticket % self.SCALAR_SLOTS))
+        return self._ring[ticket % self.SCALAR_SLOTS][2]
 
     def close(self):
         if not getattr(self, "closed", True) and getattr(self, "_h", None):

@@ -148,6 +148,19 @@ def test_step_scalars_pipeline(sb):
     with pytest.raises(sb.SnkError):
         env.wait_scalars(tickets[0])          # long gone
     got[tickets[-1]] = tuple(x.copy() for x in env.wait_scalars(tickets[-1]))
+    # a second pass that reads as late as the ring allows: no slot is recycled early
+    more = [ref.gen_actions(T + t, 11).cpu().numpy() for t in range(12)]
+    for t in range(12):
+        _, r, d, _ = ref.step(more[t])
+        want.append((r.cpu().numpy(), d.cpu().numpy().astype(np.uint8), ref.num_alive.cpu().numpy(),
+                     ref.episode_return.cpu().numpy(), ref.episode_len.cpu().numpy()))
+        tickets.append(env.step_scalars_async(more[t]))
+        if t >= env.SCALAR_SLOTS - 1:
+            tk = tickets[-env.SCALAR_SLOTS]
+            got[tk] = tuple(x.copy() for x in env.wait_scalars(tk))
+    for tk in tickets[-(env.SCALAR_SLOTS - 1):]:
+        got[tk] = tuple(x.copy() for x in env.wait_scalars(tk))
+    T = T + 12
     for t in range(T):
         r, d, n, er, el = got[tickets[t]]
         assert r.dtype == np.float32 and np.array_equal(r, want[t][0]) and np.array_equal(d, want[t][1]) and np.array_equal(n, want[t][2]), t
