@@ -1,4 +1,4 @@
-"""Small-image configurations under the three forms of the lane path (SNK_LANE): which one should be the default."""
+"""Small-image configurations under the three forms of the lane path (SNK_DEBUG=lane=...): which one should be the default."""
 import sys, os, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -12,5 +12,5 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     short(1048576, size=10, n_snakes=3, rules="cut", reps=1)
 else:
     for v in ("ws", "split", "fused"):
-        print("== SNK_LANE=%s" % v, flush=True)
-        subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, SNK_LANE=v))
+        print("== lane=%s" % v, flush=True)
+        subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, SNK_DEBUG="lane=" + v))
