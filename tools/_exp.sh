@@ -1,1 +1,3 @@
-timeout 1000 python tools/selfplay_curve.py 1 10 32 1e7 gpurun_out/ppo_single_10x10_1gpu > gpurun_out/ppo_single_10x10_1gpu.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/ppo_single_10x10_1gpu.log | cut -c1-500
+python -m pytest tests -m gpu -q > gpurun_out/r02_final3_pytest_gpu.txt 2>&1; tail -2 gpurun_out/r02_final3_pytest_gpu.txt
+python bench.py > gpurun_out/r02_final3_bench.json 2> gpurun_out/r02_final3_bench.err; echo "bench rc=$?"; cut -c1-260 gpurun_out/r02_final3_bench.json
+python -c "import __graft_entry__ as g; g.smoke()"
