@@ -397,6 +397,7 @@ class SnakeVecEnv(object):
             self._graphs = {}
             self._L.snk_destroy(self._h)
             self._h = None
+            self._ring = None   # views of pinned memory the library has just freed
         self.closed = True
 
     def __del__(self):
