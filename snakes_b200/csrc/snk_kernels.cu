@@ -784,9 +784,9 @@ __global__ void __launch_bounds__(64) k_step_lane(const Params p) {
 #endif
   if (!have_image) mbar_wait(&s_bar[warp], 0);  // never leave with a bulk copy into our shared memory in flight
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next launch may start its prologue
-  if (lane == 0) bulk_wait_all();
-  reduce_lane_stats(p, st, errs, s_stats, lane);
+  reduce_lane_stats(p, st, errs, s_stats, lane);  // (the last images drain while the statistics are folded)
   publish_stats(p, s_stats, tid);
+  if (lane == 0) bulk_wait_all();
 }
 
 template <int RULES>

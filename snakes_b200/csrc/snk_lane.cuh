@@ -444,7 +444,10 @@ __device__ __forceinline__ void lane_step(const Params& p, long long e, bool val
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     if (env.len[s] == 0) empty |= 1u << s;
-    else if (__ldg(p.cellinfo + env.head[s]) >> 31) oob |= 1u << s;
+    else {  // outside the board (:150-152), by arithmetic: a table load here sits on every batch's critical path
+      const u32 px = ((u32)env.head[s] * p.magicV) >> 16, py = (u32)env.head[s] - px * (u32)V;
+      if (px - 1u >= (u32)p.D || py - 1u >= (u32)p.D) oob |= 1u << s;
+    }
   }
   int live_head[S];  // head of a live snake, or an id no cell has: one compare per segment and snake in the walks
 #pragma unroll
