@@ -1,3 +1,2 @@
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_forms.py tests/test_gpu_fullsize.py -m gpu -x -q > gpurun_out/s18_pytest.txt 2>&1; tail -2 gpurun_out/s18_pytest.txt
-SNK_LIB=variants/libsnk_base.so python tools/ab.py short c2 > gpurun_out/s18_ab_base.txt 2>&1; cut -c1-110 gpurun_out/s18_ab_base.txt
-python tools/ab.py short c2 c3 long > gpurun_out/s18_ab_new.txt 2>&1; cut -c1-110 gpurun_out/s18_ab_new.txt
+python -m pytest tests -m gpu -q > gpurun_out/r02_final4_pytest_gpu.txt 2>&1; tail -2 gpurun_out/r02_final4_pytest_gpu.txt
+python bench.py --steps 20 --warmup 5 > gpurun_out/r02_final4_bench_20steps.json 2> gpurun_out/r02_final4_bench.err; echo "bench rc=$?"; cut -c1-240 gpurun_out/r02_final4_bench_20steps.json
