@@ -135,6 +135,27 @@ def time_cpu_path(seconds, n_procs=None, steps=None, warmup_steps=20):
     return {"env_steps_per_s": n * n_procs / dt, "vec_steps": n, "seconds": dt, "procs": n_procs, "kind": kind, "source": src}
 
 
+def time_reference_inprocess(seconds=2.0):
+    """The reference's own SnakeEnv.step in this process, one env, one core (the raw in-process figure
+    beside the SubprocVecEnv one); None when no reference tree is on the box."""
+    _oracle_path()
+    import numpy as np
+    import ref_loader
+    if not ref_loader.available():
+        return None
+    env = ref_loader.make_env(RULES, N_SNAKES, SIZE, np.random.RandomState(0))
+    env.reset()
+    rng = np.random.RandomState(1)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < seconds:
+        _, _, done, _ = env.step(tuple(int(x) for x in rng.randint(0, 5, size=N_SNAKES)))
+        if done:
+            env.reset()
+        n += 1
+    return n / (time.perf_counter() - t0)
+
+
 def time_c_oracle(seconds=3.0, n=4096):
     """The C restatement on one core (context only: a far stronger CPU baseline than the reference's Python)."""
     _oracle_path()
@@ -420,6 +441,22 @@ def run_ours(args):
         stats = stats_local
     g_warm.close(); g_main.close()
 
+    # ---- the same stream with the action generator in the loop (report both): k_gen_actions + step kernel
+    # per step, issued eagerly (two C calls per step; the device is the slower side)
+    Kg = min(K, 400)
+    for t in range(10):
+        env.step_async(env.gen_actions(5000 + t, 1, out=acts[0])); env._pending = False
+    barrier()
+    ga0, ga1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ga0.record()
+    for t in range(Kg):
+        env.step_async(env.gen_actions(5010 + t, 1, out=acts[t % n_act])); env._pending = False
+    ga1.record()
+    barrier()
+    ms_gen = max_over_ranks(ga0.elapsed_time(ga1))
+    with_action_gen = {"value": float(N) * world * Kg * S / (ms_gen * 1e-3), "unit": UNIT, "us_per_step": ms_gen / Kg * 1e3, "steps": Kg,
+                       "note": "k_gen_actions (Philox uniform actions, N*S bytes) + step kernel per step, eager launches"}
+
     # ---- second action stream: fruit-seeking policy computed on the device every step (one extra small
     # kernel per step, inside the timed region and inside the graph); snakes get long, resets get rare
     Ks = max(50, K // 4)
@@ -592,6 +629,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_env_step": alg_bytes, "env_steps_per_launch": N,
                          "launch_us": launch_s * 1e6},
             "episode_stats": stats,
+            "with_action_gen": with_action_gen,
             "scripted_policy": scripted,
         }
         if collective:
@@ -605,6 +643,9 @@ def run_ours(args):
                 "value": r["env_steps_per_s"] * S, "unit": UNIT, "cores": cores, "kind": r["kind"],
                 "sample": _cpu_sample_text(r), "c_oracle_1core": time_c_oracle(2.0) * S,
             }
+            inproc = time_reference_inprocess(2.0)
+            if inproc is not None:
+                line["cpu_baseline"]["reference_inprocess_1core"] = inproc * S
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -1,2 +1,7 @@
-python -m pytest tests -m gpu -q > gpurun_out/r02_final4_pytest_gpu.txt 2>&1; tail -2 gpurun_out/r02_final4_pytest_gpu.txt
-python bench.py --steps 20 --warmup 5 > gpurun_out/r02_final4_bench_20steps.json 2> gpurun_out/r02_final4_bench.err; echo "bench rc=$?"; cut -c1-240 gpurun_out/r02_final4_bench_20steps.json
+python bench.py --steps 400 --warmup 40 --no-configs --cpu-seconds 4 > gpurun_out/s19_bench.json 2> gpurun_out/s19_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/s19_bench.err
+python - <<'PY'
+import json
+d = json.load(open('gpurun_out/s19_bench.json'))
+print({k: d[k] for k in ('value', 'ms_per_step')}, d['roofline']['frac'])
+print(d['with_action_gen']); print(d['cpu_baseline'])
+PY
